@@ -1,0 +1,174 @@
+"""ctypes binding of include/cmixb200.h.
+
+`Predictor` mirrors the reference's `class Predictor` (reference src/predictor.h:17-53):
+Predict() / Perceive(bit) / Pretrain(bit), plus the bulk compress-direction call the
+reference's Compress() loop (src/runner.cpp:101-119) maps to.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+N_EXT = 2022
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcmixb200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lib = None
+
+
+def build_library(force=False):
+    """Compile cmix_b200/csrc/engine.cu for sm_100a into libcmixb200.so (in-tree)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "cmixb200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + [os.path.join(CSRC, "engine.cu"), "-o", LIB_PATH]
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("cmix_b200: %s is missing - run __graft_entry__.build() (nvcc, sm_100a); "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp = c.c_void_p
+    lib.cmixb200_create.argtypes = [vp, c.c_char_p, c.c_int, c.POINTER(vp)]
+    lib.cmixb200_create.restype = c.c_int
+    lib.cmixb200_destroy.argtypes = [vp]
+    lib.cmixb200_destroy.restype = None
+    lib.cmixb200_predict.argtypes = [vp]
+    lib.cmixb200_predict.restype = c.c_float
+    lib.cmixb200_perceive.argtypes = [vp, c.c_int]
+    lib.cmixb200_pretrain.argtypes = [vp, c.c_int]
+    lib.cmixb200_feed_external_bit.argtypes = [vp, vp]
+    lib.cmixb200_feed_external_byte.argtypes = [vp, vp]
+    lib.cmixb200_code_bytes.argtypes = [vp, vp, c.c_size_t, vp, vp, vp]
+    lib.cmixb200_code_bytes_device.argtypes = [vp, vp, c.c_size_t, vp, vp, vp]
+    lib.cmixb200_code_batch_device.argtypes = [vp, c.c_int, vp, c.c_size_t, vp, vp, vp]
+    lib.cmixb200_pretrain_bytes.argtypes = [vp, vp, c.c_size_t]
+    lib.cmixb200_last_error.restype = c.c_char_p
+    lib.cmixb200_kernel_launches.argtypes = [vp]
+    lib.cmixb200_kernel_launches.restype = c.c_ulonglong
+    lib.cmixb200_mix_stream.argtypes = [vp]
+    lib.cmixb200_mix_stream.restype = vp
+    lib.cmixb200_debug_fetch.argtypes = [vp, c.c_int, vp, c.c_size_t]
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError("cmix_b200.%s failed (%d): %s" % (what, rc, lib.cmixb200_last_error().decode()))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+class Predictor:
+    """Mirror of the reference `Predictor` (src/predictor.h:17-53) on one B200."""
+
+    def __init__(self, vocab, dictionary_path=None, device=0):
+        self._lib = load_library()
+        v = np.ascontiguousarray(np.asarray(vocab, dtype=np.uint8))
+        assert v.size == 256
+        h = ctypes.c_void_p()
+        d = dictionary_path.encode() if dictionary_path else None
+        _check(self._lib, self._lib.cmixb200_create(v.ctypes.data, d, int(device), ctypes.byref(h)), "create")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cmixb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # --- the reference surface -------------------------------------------------
+    def Predict(self):
+        p = self._lib.cmixb200_predict(self._h)
+        if p < 0:
+            raise RuntimeError("cmix_b200.predict failed: %s" % self._lib.cmixb200_last_error().decode())
+        return p
+
+    def Perceive(self, bit):
+        _check(self._lib, self._lib.cmixb200_perceive(self._h, int(bit)), "perceive")
+
+    def Pretrain(self, bit):
+        _check(self._lib, self._lib.cmixb200_pretrain(self._h, int(bit)), "pretrain")
+
+    # --- replayed model streams ------------------------------------------------
+    def feed_external_bit(self, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.uint16)
+        assert codes.size == N_EXT
+        _check(self._lib, self._lib.cmixb200_feed_external_bit(self._h, codes.ctypes.data), "feed_external_bit")
+
+    def feed_external_byte(self, ppmd):
+        ppmd = np.ascontiguousarray(ppmd, dtype=np.float32)
+        assert ppmd.size == 256
+        _check(self._lib, self._lib.cmixb200_feed_external_byte(self._h, ppmd.ctypes.data), "feed_external_byte")
+
+    # --- bulk paths --------------------------------------------------------------
+    def code_bytes(self, data, ext=None, ppmd=None):
+        """Host buffers in, host probabilities out (one float per bit)."""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        n = data.size
+        if ext is not None:
+            ext = np.ascontiguousarray(ext, dtype=np.uint16)
+            assert ext.size == n * 8 * N_EXT
+        if ppmd is not None:
+            ppmd = np.ascontiguousarray(ppmd, dtype=np.float32)
+            assert ppmd.size == n * 256
+        out = np.empty(n * 8, dtype=np.float32)
+        _check(self._lib, self._lib.cmixb200_code_bytes(self._h, _ptr(data), n, _ptr(ext), _ptr(ppmd), _ptr(out)), "code_bytes")
+        return out
+
+    def code_bytes_device(self, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out):
+        """All arguments are torch CUDA tensors (or None) already resident in HBM."""
+        _check(self._lib, self._lib.cmixb200_code_bytes_device(self._h, _ptr(d_bytes), n_bytes, _ptr(d_ext), _ptr(d_ppmd),
+                                                                _ptr(d_p_out)), "code_bytes_device")
+
+    def pretrain_bytes(self, data):
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        _check(self._lib, self._lib.cmixb200_pretrain_bytes(self._h, data.ctypes.data, data.size), "pretrain_bytes")
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.cmixb200_kernel_launches(self._h))
+
+    @property
+    def mix_stream(self):
+        return int(self._lib.cmixb200_mix_stream(self._h) or 0)
+
+    def debug_fetch(self, what, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        _check(self._lib, self._lib.cmixb200_debug_fetch(self._h, what, out.ctypes.data, out.nbytes), "debug_fetch")
+        return out
+
+
+def code_batch_device(preds, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out):
+    """Advance len(preds) independent predictors by n_bytes each in one launch set."""
+    lib = load_library()
+    n = len(preds)
+    VP = ctypes.c_void_p * n
+    hs = VP(*[p._h.value for p in preds])
+    by = VP(*[_ptr(t) for t in d_bytes])
+    ex = VP(*[_ptr(t) for t in d_ext]) if d_ext is not None else None
+    pp = VP(*[_ptr(t) for t in d_ppmd]) if d_ppmd is not None else None
+    po = VP(*[_ptr(t) for t in d_p_out])
+    _check(lib, lib.cmixb200_code_batch_device(hs, n, by, n_bytes, ex, pp, po), "code_batch_device")

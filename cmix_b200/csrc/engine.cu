@@ -1,0 +1,709 @@
+// cmix_b200/csrc/engine.cu — host side of the B200 predictor engine + the C-ABI
+// declared in include/cmixb200.h.
+//
+// Host responsibilities (everything numeric runs in the kernels):
+//  * build the read-only tables the reference builds with libm at start-up
+//    (logit LUT sigmoid.cpp:5-10, SSE stretch/squash sse.cpp:112-135, Adam bias
+//    corrections lstm-layer.cpp:17-30, per-bit decay mixer.cpp:58) with the same
+//    glibc the oracle uses, and upload them;
+//  * draw the initial LSTM weights / Indirect offsets from glibc's rand() stream
+//    seeded with 0xDEADBEEF in the reference's construction order
+//    (predictor.cpp:26-36);
+//  * allocate the ~6 GB of per-stream HBM state and launch the three bulk
+//    kernels (small | lstm | mix) on separate CUDA streams, or their lock-step
+//    halves for Predict()/Perceive().
+// There is NO CPU fallback: every entry point fails with CMIXB200_ERR_CUDA if
+// the device or a kernel is unavailable.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cmixb200.h"
+#include "exact_math.h"
+#include "lstm.cuh"
+#include "mixer.cuh"
+#include "small_models.cuh"
+#include "state.h"
+
+using namespace cmixb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      g_last_error = buf_;                                                               \
+      return CMIXB200_ERR_CUDA;                                                          \
+    }                                                                                    \
+  } while (0)
+
+// states/nonstationary.cpp:3 — 256x2 next-state table as hex, [state][bit].
+const char kNonstatHex[] =
+    "020c90050705190e3605101d1a8ca9051018540410250a620ad42d25c9001cca"
+    "2017b78806d9bc2608251545083d380d16251b42558c23296bc7085b66d96411"
+    "68175e05602f2bb02e3016276b331833fbf8190136223594463a5617163d4617"
+    "243f3d3f07053e415ad84369442296056049462f484a494b2e3f4a311459244f"
+    "148a3e51aa0e5245542215e960480ad42c3b2c3b3a4c3a4c4b3d3c3116274d59"
+    "13413e5b5ad996b95e225c7f6017a7cf92934d635d660b65616967f968221341"
+    "6a397a7b1627306d00cb0b6f03536c70722219f57422132771e63077a6bc3e79"
+    "8c60751b7c04c2e72a228d7fa4b33f81ebcc6b837d7f6ed98604848512f5c90e"
+    "3eaf308b80b70b97891e23cc87049004af958ed93eb73033c901bdab91855fb2"
+    "962198995fc3a7b3234240ac9a096b9b9c9d1bef9e09269fa0a143c2a221508f"
+    "a3b9c9f9a609a53400e7a88c6ebc64cfadb0b121aebc150097c0b5451b9afc8a"
+    "4221bd09e48f1f28be5ab8b9bc793fbbba948d34c15380bf72b6cddcc53480c3"
+    "92d4c43464d782c7c685ecefcee9fccb64cb034292fe5bcfb9c2e501d1e65fd3"
+    "6411d6d8641182d740e1c9ccdaef92dba6e6f901deccc8df8601a7d7e2ae83e3"
+    "ddf740ede84557e71341eedc230cc811b4ad43d91c65c5d5f0f1fcfdf2dc6ca4"
+    "f3f4c9a4f62978d5c9349a017e377376737619d826c3a7d7148a400f1c580e11";
+
+// predictor.cpp:201-356: selector and learning rate of each of the 47 mixers.
+const int kSel[N_MIXERS] = {
+    S_BC0, S_BC0, S_BC1, S_BC1, S_BC2, S_BC3, S_RB2, S_RB3, S_ZERO, S_LINEBREAK, S_LONGEST, S_WRT, S_AUX,
+    S_IV0, S_IV1, S_IV2, S_BC_ALNUM, S_IV3, S_IV4, S_BC_W2, S_IV6, S_IVH, S_BC_W3, S_BC_RB1, S_COMB0, S_COMB1,
+    S_ZERO, S_ZERO, S_LONGBIT, S_LONGBIT, S_LONGBIT, S_RB0, S_RB1, S_RB2, S_LONGEST, S_WRT,
+    S_IV0, S_IV1, S_IV2, S_IV3, S_IV4, S_IV6, S_IVH, S_BC_W2, S_BC_ALNUM, S_BC_W3,
+    S_ZERO};
+const double kLr[N_MIXERS] = {
+    0.005, 0.0005, 0.005, 0.0005, 0.005, 0.002, 0.002, 0.005, 0.00005, 0.0007, 0.0005, 0.002, 0.0005,
+    0.001, 0.001, 0.001, 0.005, 0.001, 0.001, 0.005, 0.001, 0.001, 0.005, 0.005, 0.005, 0.003,
+    0.005, 0.0005, 0.005, 0.0005, 0.00001, 0.005, 0.005, 0.005, 0.0005, 0.002,
+    0.001, 0.001, 0.001, 0.001, 0.001, 0.001, 0.001, 0.001, 0.001, 0.001,
+    0.0003};
+// number of distinct values each selector can take (bounds the row table)
+u32 SelRange(int s) {
+  switch (s) {
+    case S_ZERO: return 1;
+    case S_LONGBIT: case S_RB0: case S_RB1: case S_RB2: case S_RB3: return 256;
+    case S_LINEBREAK: return 100;
+    case S_LONGEST: return 8;
+    case S_WRT: return 0xFFEFCF + 1;
+    case S_AUX: return 16;
+    case S_IV0: case S_IV1: return 256;
+    case S_IV2: return 128;
+    case S_IV3: return 1024;
+    case S_IV4: return 32768;
+    case S_IV6: return 512;
+    case S_IVH: return 16384;
+    case S_BC0: return 256;
+    case S_BC1: case S_BC2: return 65536;
+    case S_BC3: return 16384;
+    case S_BC_ALNUM: case S_BC_W2: case S_BC_W3: return 32768;
+    case S_BC_RB1: case S_COMB0: case S_COMB1: return 65536;
+  }
+  return 1;
+}
+
+int IntervalMap(int which, int c) {   // predictor.cpp:223-304
+  static const int t1[] = {1, 32, 64, 128, 255, 142, 138, 140, 137, 97};
+  static const int t2[] = {41, 92, 124, 58, 11, 46, 36, 47, 64, 4, 61, 97, 125, 45, 48};
+  static const char m4[] = "2313301233001333" "3333333333303333" "3202132133332302"
+                           "1111111111322322" "2200231212222200" "2222222230232023";
+  static const char m6[] = "0020560602043000" "0000000000000000" "2414474737223531"
+                           "1111111111053355" "0557501545006071" "3374557022544746";
+  int v = 0;
+  switch (which) {
+    case 0: for (int t : t1) v += c < t; return v;
+    case 1: for (int t : t2) v += c < t; return v;
+    case 2: return ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c >= 0x80) ? 1 : 0;
+    case 3: return c < 96 ? m4[c] - '0' : (c < 208 ? 1 : 0);
+    default: return c < 96 ? m6[c] - '0' : (c < 128 ? 5 : (c < 208 ? 6 : 7));
+  }
+}
+
+struct GlibcRand {   // the rand() stream of one Predictor (TYPE_3 additive feedback, as rand())
+  char statebuf[128];
+  struct random_data rd;
+  explicit GlibcRand(unsigned seed) {
+    memset(&rd, 0, sizeof rd); memset(statebuf, 0, sizeof statebuf);
+    initstate_r(seed, statebuf, sizeof statebuf, &rd);
+  }
+  int next() { int32_t r; random_r(&rd, &r); return r; }
+};
+
+__global__ void fill_f32(float* p, size_t n, float v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_u32(u32* p, size_t n, u32 v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_sse_rows(u16* p, size_t vol, int Wi) {   // SSEi<7>::Init (sse.cpp:25-31), 8-u16 pitch
+  const int SCw = (32768 - Wi) / 6, INC = Wi / 2 + 8192;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < vol * 8; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i & 7);
+    p[i] = k < 7 ? (u16)(INC + k * SCw) : 0;
+  }
+}
+
+struct SharedTables {   // one per process/device
+  bool ready = false;
+  int device = -1;
+  float* d_logit = nullptr; float* d_lut12 = nullptr; u16* d_st = nullptr; u16* d_sq = nullptr; float* d_adam = nullptr;
+  Tables T;
+};
+SharedTables g_tables;
+
+int BuildSharedTables(int device) {
+  if (g_tables.ready && g_tables.device == device) return CMIXB200_OK;
+  std::vector<float> logit(100001);
+  for (int i = 0; i < 100001; ++i) {
+    float p = (i + 0.5f) / 100001;
+    logit[i] = logf(p / (1 - p));
+  }
+  auto Logit = [&](float p) { int idx = p * 100001; if (idx >= 100001) idx = 100000; else if (idx < 0) idx = 0; return logit[idx]; };
+  std::vector<float> lut12(4097);
+  const float cf = 1.0 / 4095;
+  for (int c = 0; c <= 4096; ++c) {
+    float p = c == 4096 ? 0.5f : c * cf;
+    if (p < 1.0e-4f) p = 1.0e-4f; else if (p > 1 - 1.0e-4f) p = 1 - 1.0e-4f;
+    lut12[c] = Logit(p);
+  }
+  // SSE stretch/squash (sse.cpp:78-135), double libm as the reference
+  std::vector<u16> st(32768, 0), sq(32768, 0);
+  {
+    const double log2e = 1.44269504088896340736;
+    const double st_coef = (16384 - 1) / (log2e * log((double)(32768 - 1)));
+    const double sq_coef = 1.0 / st_coef;
+    for (unsigned i = 1; i < 32768; ++i) {
+      double a = double(int(i) - 16384) * sq_coef;
+      unsigned p = (1.0 / (1.0 + exp(a / log2e))) * 32768;
+      sq[i] = (u16)p;
+    }
+    unsigned x = 0;
+    for (unsigned i = 1; i < 32768; ++i) {
+      double pr = double(i) / 32768;
+      unsigned s = (log2e * log((1 - pr) / pr)) * st_coef + 16384;
+      st[i] = (u16)s;
+      if (s != st[x]) { unsigned y = i - 1; sq[st[x]] = (u16)((x + y + 1) / 2); x = i; }
+    }
+  }
+  // Adam step scalars (lstm-layer.cpp:11-32) for update_steps_ = 0..3000
+  std::vector<float> adam(3001 * 4, 0.0f);
+  {
+    const float beta1 = 0.025, beta2 = 0.9999;
+    const float learning_rate = 0.03;
+    const unsigned long long update_limit = 3000;
+    for (int ti = 0; ti <= 3000; ++ti) {
+      float t = ti;
+      float alpha, bc1, bc2;
+      if (t < update_limit) {
+        alpha = learning_rate * 0.1f / sqrt(5e-5f * t + 1.0f);
+        bc1 = (float)(1.0f - pow(beta1, t));
+        bc2 = (float)(1.0f - pow(beta2, t));
+      } else {
+        alpha = learning_rate * 0.1f / sqrt(5e-5f * update_limit + 1.0f);
+        bc1 = (float)(1.0f - pow(beta1, update_limit));
+        bc2 = (float)(1.0f - pow(beta2, update_limit));
+      }
+      adam[ti * 4] = alpha; adam[ti * 4 + 1] = bc1; adam[ti * 4 + 2] = bc2;
+    }
+  }
+  CK(cudaMalloc(&g_tables.d_logit, logit.size() * 4));
+  CK(cudaMemcpy(g_tables.d_logit, logit.data(), logit.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&g_tables.d_lut12, lut12.size() * 4));
+  CK(cudaMemcpy(g_tables.d_lut12, lut12.data(), lut12.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&g_tables.d_st, st.size() * 2));
+  CK(cudaMemcpy(g_tables.d_st, st.data(), st.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&g_tables.d_sq, sq.size() * 2));
+  CK(cudaMemcpy(g_tables.d_sq, sq.data(), sq.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&g_tables.d_adam, adam.size() * 4));
+  CK(cudaMemcpy(g_tables.d_adam, adam.data(), adam.size() * 4, cudaMemcpyHostToDevice));
+  g_tables.T.logit = g_tables.d_logit;
+  g_tables.T.lut12 = g_tables.d_lut12;
+  g_tables.T.stretch_min = Logit(0);
+  g_tables.T.stretch_max = Logit(1);
+  // constant-memory tables
+  u8 nonstat[512], runmap[512], ivmap[5][256], msel[N_MIXERS];
+  auto hv = [](char c) { return c <= '9' ? c - '0' : c - 'a' + 10; };
+  for (int i = 0; i < 512; ++i) nonstat[i] = (u8)(hv(kNonstatHex[2 * i]) * 16 + hv(kNonstatHex[2 * i + 1]));
+  for (int i = 0; i < 512; ++i) {   // run-map.cpp:3-20
+    int state = i / 2;
+    if (i % 2 == 0) { if (state < 127) ++state; else if (state >= 128) state = 0; }
+    else { if (state < 128) state = 128; else if (state < 255) ++state; }
+    runmap[i] = (u8)state;
+  }
+  for (int m = 0; m < 5; ++m) for (int c = 0; c < 256; ++c) ivmap[m][c] = (u8)IntervalMap(m, c);
+  for (int i = 0; i < N_MIXERS; ++i) msel[i] = (u8)kSel[i];
+  CK(cudaMemcpyToSymbol(c_nonstat, nonstat, sizeof nonstat));
+  CK(cudaMemcpyToSymbol(c_runmap, runmap, sizeof runmap));
+  CK(cudaMemcpyToSymbol(c_ivmap, ivmap, sizeof ivmap));
+  CK(cudaMemcpyToSymbol(c_mixer_sel, msel, sizeof msel));
+  CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
+  CK(cudaFuncSetAttribute(mix_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
+  CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
+  CK(cudaFuncSetAttribute(lstm_perceive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
+  g_tables.ready = true;
+  g_tables.device = device;
+  return CMIXB200_OK;
+}
+
+}  // namespace
+
+struct cmixb200_predictor {
+  int device = 0;
+  StreamState* d_st = nullptr;
+  StreamState h;                       // host mirror of the pointer/parameter fields
+  std::vector<void*> allocs;
+  cudaStream_t s_small = nullptr, s_lstm = nullptr, s_mix = nullptr;
+  ChunkArgs* d_args = nullptr;
+  // chunk scratch
+  size_t scratch_bits = 0;
+  float* d_small_x = nullptr; u32* d_sel = nullptr; float* d_lstm_x = nullptr; float* d_decay = nullptr; float* d_p = nullptr;
+  u8* d_bytes = nullptr; u16* d_ext = nullptr; float* d_ppmd = nullptr; size_t stage_bytes = 0;
+  // lock-step state
+  u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
+  u32 bit_context = 1;                 // partial byte incl. leading 1 (ContextManager::bit_context_)
+  u16* d_ext_bit = nullptr; bool ext_bit_valid = false;
+  float* d_ppmd_byte = nullptr; bool ppmd_byte_valid = false;
+  unsigned long long launches = 0;
+  u8 vocab[256];
+  int V = 0;
+
+  template <class T> int Alloc(T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T)));
+    if (zero) CK(cudaMemset(q, 0, n * sizeof(T)));
+    allocs.push_back(q);
+    *p = (T*)q;
+    return CMIXB200_OK;
+  }
+};
+
+namespace {
+
+#define TRY(x) do { int r_ = (x); if (r_ != CMIXB200_OK) return r_; } while (0)
+
+int InitDirect(cmixb200_predictor* P, DirectTable& d, int limit, float delta, u64 rows, bool hashed) {
+  d.limit = limit; d.delta = delta; d.divisor = 1.0 / (limit + delta); d.rows = rows; d.hashed = hashed; d.index = 0;
+  TRY(P->Alloc(&d.pred, rows * 256, false));
+  fill_f32<<<1024, 256>>>(d.pred, rows * 256, 0.5f);
+  TRY(P->Alloc(&d.count, rows * 256));
+  d.checksum = nullptr;
+  if (hashed) TRY(P->Alloc(&d.checksum, rows));
+  return CMIXB200_OK;
+}
+
+int BuildStream(cmixb200_predictor* P) {
+  StreamState& h = P->h;
+  memset(&h, 0, sizeof h);
+  GlibcRand rng(0xDEADBEEF);
+  // ---------------- mixers ----------------
+  for (int i = 0; i < N_MIXERS; ++i) {
+    MixerState& m = h.mixer[i];
+    m.sel = kSel[i];
+    m.lr = (float)kLr[i];
+    if (i < N_L0) { m.n_in = N_INPUTS; m.n_extra = i; m.pitch = ROW_PITCH_L0; }
+    else if (i < N_L0 + N_L1) { m.n_in = L1_IN; m.n_extra = i - N_L0; m.pitch = ROW_PITCH_L1; }
+    else { m.n_in = L2_IN; m.n_extra = 0; m.pitch = ROW_PITCH_L2; }
+    m.table_size = SelRange(m.sel);
+    const u32 cap = m.table_size < (u32)SLOT_LIMIT ? m.table_size : (u32)SLOT_LIMIT;
+    m.n_rows = cap + 1;
+    m.n_assigned = 0;
+    m.max_steps = 1;
+    TRY(P->Alloc(&m.slot_table, m.table_size));
+    TRY(P->Alloc(&m.rows, (size_t)m.n_rows * m.pitch));
+    TRY(P->Alloc(&m.row_steps, m.n_rows));
+  }
+  // ---------------- SSE ----------------
+  {
+    SseState& S = h.sse;
+    const size_t kMix1Vol = 4ull * 256 * 8 * 79, kMix2Vol = 3ull * 2 * 256 * 256,
+                 kSm6Vol = 3ull * 128 * 256 * 256, kSm7Vol = 3ull * 32 * 256 * 255;
+    TRY(P->Alloc(&S.s6, kSm6Vol * 8, false));
+    TRY(P->Alloc(&S.s7, kSm7Vol * 8, false));
+    fill_sse_rows<<<2048, 256>>>(S.s6, kSm6Vol, 0);
+    fill_sse_rows<<<2048, 256>>>(S.s7, kSm7Vol, 8192);
+    TRY(P->Alloc(&S.x1, kMix1Vol, false));
+    TRY(P->Alloc(&S.x2, kMix2Vol, false));
+    fill_u32<<<512, 256>>>((u32*)S.x1, kMix1Vol, 7649 + 16384);
+    fill_u32<<<512, 256>>>((u32*)S.x2, kMix2Vol, 2561 + 16384);
+    S.st = g_tables.d_st; S.sq = g_tables.d_sq;
+    S.j = 1; S.pc = 0; S.ffl = 0;
+  }
+  // ---------------- small models + contexts (construction order == rand() order) ----------------
+  {
+    SmallState& s = h.small;
+    memcpy(s.vocab, P->vocab, 256);
+    s.bit_context = 1; s.long_bit_context = 1;
+    TRY(P->Alloc(&s.history, 100000000ull));
+    TRY(P->Alloc(&s.shared_map, 256ull * 8000000ull));
+    s.br_cap = 1u << 22;
+    TRY(P->Alloc(&s.br_char, s.br_cap));
+    TRY(P->Alloc(&s.br_dist, s.br_cap));
+    static const int ih[11][4] = {{1, 8, 1, 8}, {2, 8, 1, 8}, {1, 8, 2, 8}, {2, 8, 2, 8}, {1, 8, 3, 8}, {3, 8, 1, 8},
+                                  {4, 6, 4, 8}, {5, 5, 5, 5}, {1, 8, 4, 8}, {1, 8, 5, 6}, {6, 4, 6, 4}};
+    for (int i = 0; i < 11; ++i) {
+      IHashState& x = s.ihash[i];
+      x.h1 = ih[i][1]; x.h2 = ih[i][3];
+      x.size1 = (u32)(1ull << (ih[i][1] * ih[i][0]));
+      x.size = 1ull << (ih[i][3] * ih[i][2]);
+      TRY(P->Alloc(&x.hashes, x.size1));
+    }
+    // Bracket (model 0)
+    for (int i = 0; i < 256; ++i) s.bracket_bm.probs[i] = 1.0 / 256;
+    s.bracket_bm.top = 255;
+    TRY(P->Alloc(&s.bk_first, 256 * 200, false));
+    TRY(P->Alloc(&s.bk_second, 256 * 200, false));
+    fill_u32<<<64, 256>>>(s.bk_first, 256 * 200, 1);
+    fill_u32<<<64, 256>>>(s.bk_second, 256 * 200, 256);
+    TRY(InitDirect(P, s.direct_bracket, 30, 0, 257 * 256, false));
+    auto init_ind = [&](IndirectState& m, bool run, float delta) {
+      m.run = run; m.divisor = 1.0 / delta; m.map_index = 0;
+      m.map_offset = (u64)rng.next() % (2048000000ull - 257);     // indirect.cpp:10
+      for (int i = 0; i < 256; ++i) m.pred[i] = !run ? 0.5f : (float)(i < 128 ? (128.0 - i) / 256 : i / 256.0);
+    };
+    auto init_match = [&](MatchState& m, int limit, float delta, u64 map_size) -> int {
+      m.limit = limit; m.delta = delta; m.divisor = 1.0 / (limit + delta);
+      m.map_size = map_size; m.bit_pos = 128;
+      TRY(P->Alloc(&m.map, map_size));
+      for (int i = 0; i < 256; ++i) { m.pred[i] = 0.5 + (i + 0.5) / 512; m.count[i] = 0; }
+      return CMIXB200_OK;
+    };
+    init_ind(s.indirect[0], false, 300);
+    for (int i = 0; i < 18; ++i) init_ind(s.indirect[1 + i], false, 200);
+    for (int i = 0; i < 6; ++i) {
+      TRY(init_match(s.match[i], 200, 0.5, 10000000));
+      if (i == 1) { init_ind(s.indirect[19], true, 200); TRY(InitDirect(P, s.dhash_word, 30, 0, 500000, true)); }
+    }
+    TRY(InitDirect(P, s.direct_o[0], 30, 0, 1, false));
+    TRY(InitDirect(P, s.direct_o[1], 30, 0, 256, false));
+    TRY(InitDirect(P, s.direct_o[2], 30, 0, 65536, false));
+    TRY(InitDirect(P, s.dhash_o3, 30, 0, 100000, true));
+    static const u64 msize[10] = {1, 256, 65536, 20000000, 20000000, 20000000, 20000000, 20000000, 1048576, 20000000};
+    for (int i = 0; i < 10; ++i) TRY(init_match(s.match[6 + i], 200, 0.5, msize[i]));
+    for (int i = 0; i < 11; ++i) init_ind(s.indirect[20 + i], false, 400);
+    for (int i = 0; i < 256; ++i) s.ppmd_bm.probs[i] = 1.0 / 256;
+    s.ppmd_bm.top = 255;
+  }
+  // ---------------- LSTM (lstm.cpp:6-32, lstm-layer.cpp:34-60) ----------------
+  {
+    LstmState& L = h.lstm;
+    const int V = P->V, C = LSTM_CELLS, H = LSTM_HORIZON;
+    L.V = V; L.epoch = 0;
+    memcpy(L.vocab, P->vocab, 256);
+    { int k = 0; for (int i = 0; i < 256; ++i) { L.byte_map[i] = k; if (P->vocab[i]) ++k; } }
+    for (int i = 0; i < 256; ++i) L.bm.probs[i] = 1.0 / 256;
+    L.bm.top = 255;
+    L.hidden[2 * C] = 1;
+    L.adam = g_tables.d_adam;
+    TRY(P->Alloc(&L.out_w, (size_t)H * V * LSTM_HID));
+    TRY(P->Alloc(&L.output, (size_t)H * V, false));
+    fill_f32<<<64, 256>>>(L.output, (size_t)H * V, (float)(1.0 / V));
+    for (int l = 0; l < 2; ++l) {
+      LayerState& Y = L.layer[l];
+      Y.in_size = l == 0 ? V + C + 1 : V + 2 * C + 1;
+      Y.epoch = 0; Y.update_steps = 0;
+      const int row = Y.in_size + V;
+      TRY(P->Alloc(&Y.tanh_state, H * C)); TRY(P->Alloc(&Y.input_gate_state, H * C)); TRY(P->Alloc(&Y.last_state, H * C));
+      std::vector<float> inp((size_t)H * Y.in_size, 0.0f);
+      for (int e = 0; e < H; ++e) inp[(size_t)e * Y.in_size + Y.in_size - 1] = 1;
+      TRY(P->Alloc(&Y.input, inp.size(), false));
+      CK(cudaMemcpy(Y.input, inp.data(), inp.size() * 4, cudaMemcpyHostToDevice));
+      std::vector<float> w[3];
+      for (int g = 0; g < 3; ++g) w[g].assign((size_t)row * C, 0.0f);
+      const float val = sqrt(6.0f / float(V + V));
+      const float low = -val, range = 2 * val;
+      auto rnd = [&]() { return static_cast<float>(rng.next()) / static_cast<float>(RAND_MAX); };
+      for (int i = 0; i < C; ++i) {
+        for (int j = 0; j < row; ++j) {
+          w[0][(size_t)j * C + i] = low + rnd() * range;
+          w[1][(size_t)j * C + i] = low + rnd() * range;
+          w[2][(size_t)j * C + i] = low + rnd() * range;
+        }
+        w[0][(size_t)(row - 1) * C + i] = 1;
+      }
+      for (int g = 0; g < 3; ++g) {
+        GateState& G = Y.gate[g];
+        G.row = row;
+        TRY(P->Alloc(&G.w, (size_t)row * C, false));
+        CK(cudaMemcpy(G.w, w[g].data(), w[g].size() * 4, cudaMemcpyHostToDevice));
+        TRY(P->Alloc(&G.m, (size_t)row * C)); TRY(P->Alloc(&G.v, (size_t)row * C));
+        TRY(P->Alloc(&G.state, H * C)); TRY(P->Alloc(&G.norm, H * C)); TRY(P->Alloc(&G.err, H * C));
+        for (int i = 0; i < C; ++i) G.gamma[i] = 1.0f;
+      }
+    }
+  }
+  h.lstm_override = -1.0f;
+  h.last_p = 0.5f;
+  TRY(P->Alloc(&P->d_st, 1));
+  CK(cudaMemcpy(P->d_st, &h, sizeof h, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  return CMIXB200_OK;
+}
+
+int EnsureScratch(cmixb200_predictor* P, size_t n_bytes) {
+  const size_t bits = n_bytes * 8;
+  if (bits <= P->scratch_bits) return CMIXB200_OK;
+  for (void* q : {(void*)P->d_small_x, (void*)P->d_sel, (void*)P->d_lstm_x, (void*)P->d_decay, (void*)P->d_p}) if (q) cudaFree(q);
+  CK(cudaMalloc(&P->d_small_x, bits * SMALL_X_PITCH * 4));
+  CK(cudaMalloc(&P->d_sel, bits * SEL_PITCH * 4));
+  CK(cudaMalloc(&P->d_lstm_x, bits * 2 * 4));
+  CK(cudaMalloc(&P->d_decay, bits * 4));
+  CK(cudaMalloc(&P->d_p, bits * 4));
+  P->scratch_bits = bits;
+  return CMIXB200_OK;
+}
+
+void FillDecay(std::vector<float>& out, u64 steps0, size_t n_bits) {
+  out.resize(n_bits);
+  for (size_t i = 0; i < n_bits; ++i) {
+    unsigned long long steps = steps0 + i;
+    float decay = 0.9 / pow(0.0000001 * steps + 0.8, 0.8);     // mixer.cpp:58
+    out[i] = decay;
+  }
+}
+
+// Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
+int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain) {
+  const Tables T = g_tables.T;
+  small_kernel<<<n_streams, 64, 0, lead->s_small>>>(d_args, T);
+  lead->launches++;
+  if (!pretrain) {
+    lstm_kernel<<<n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
+    lead->launches++;
+    // the mixer consumes what the two producers write: order it after both
+    cudaEvent_t e1, e2;
+    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    CK(cudaEventRecord(e1, lead->s_small));
+    CK(cudaEventRecord(e2, lead->s_lstm));
+    CK(cudaStreamWaitEvent(lead->s_mix, e1, 0));
+    CK(cudaStreamWaitEvent(lead->s_mix, e2, 0));
+    mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
+    lead->launches++;
+    CK(cudaEventDestroy(e1));
+    CK(cudaEventDestroy(e2));
+  }
+  CK(cudaGetLastError());
+  return CMIXB200_OK;
+}
+
+int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u16* d_ext, const float* d_ppmd,
+               float* d_p_out, bool pretrain) {
+  if (n_bytes == 0) return CMIXB200_OK;
+  if (P->bit_context != 1) { g_last_error = "bulk coding must start on a byte boundary"; return CMIXB200_ERR_ARG; }
+  CK(cudaSetDevice(P->device));
+  TRY(EnsureScratch(P, n_bytes));
+  ChunkArgs a;
+  memset(&a, 0, sizeof a);
+  a.st = P->d_st; a.bytes = d_bytes; a.ext = d_ext; a.ppmd = d_ppmd; a.decay = P->d_decay;
+  a.small_x = P->d_small_x; a.sel = P->d_sel; a.lstm_x = P->d_lstm_x; a.p_out = d_p_out;
+  a.n_bytes = (u32)n_bytes; a.pretrain = pretrain ? 1 : 0;
+  if (!pretrain) {
+    std::vector<float> decay;
+    FillDecay(decay, P->bits_done, n_bytes * 8);
+    CK(cudaMemcpyAsync(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice, P->s_mix));
+    CK(cudaStreamSynchronize(P->s_mix));
+  }
+  CK(cudaMemcpy(P->d_args, &a, sizeof a, cudaMemcpyHostToDevice));
+  TRY(LaunchChunk(P, P->d_args, 1, pretrain));
+  CK(cudaStreamSynchronize(P->s_small));
+  if (!pretrain) { CK(cudaStreamSynchronize(P->s_lstm)); CK(cudaStreamSynchronize(P->s_mix)); P->bits_done += n_bytes * 8; }
+  return CMIXB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cmixb200_last_error(void) { return g_last_error.c_str(); }
+
+int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int device, cmixb200_predictor** out) {
+  (void)dictionary_path;   // consumed by FXCM only (fxcmv1.cpp:412-428), which is replayed, not resident
+  if (!vocab || !out) { g_last_error = "null argument"; return CMIXB200_ERR_ARG; }
+  int n_dev = 0;
+  CK(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) { g_last_error = "no such CUDA device"; return CMIXB200_ERR_CUDA; }
+  CK(cudaSetDevice(device));
+  TRY(BuildSharedTables(device));
+  cmixb200_predictor* P = new cmixb200_predictor();
+  P->device = device;
+  for (int i = 0; i < 256; ++i) { P->vocab[i] = vocab[i] ? 1 : 0; P->V += P->vocab[i]; }
+  if (P->V == 0) { delete P; g_last_error = "empty vocabulary"; return CMIXB200_ERR_ARG; }
+  int r = BuildStream(P);
+  if (r == CMIXB200_OK) {
+    cudaStreamCreateWithFlags(&P->s_small, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&P->s_lstm, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&P->s_mix, cudaStreamNonBlocking);
+    if (cudaMalloc(&P->d_args, sizeof(ChunkArgs)) != cudaSuccess || cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
+        cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
+  }
+  if (r != CMIXB200_OK) { cmixb200_destroy(P); return r; }
+  *out = P;
+  return CMIXB200_OK;
+}
+
+void cmixb200_destroy(cmixb200_predictor* P) {
+  if (!P) return;
+  cudaSetDevice(P->device);
+  cudaDeviceSynchronize();
+  for (void* q : P->allocs) cudaFree(q);
+  for (void* q : {(void*)P->d_small_x, (void*)P->d_sel, (void*)P->d_lstm_x, (void*)P->d_decay, (void*)P->d_p,
+                  (void*)P->d_bytes, (void*)P->d_ext, (void*)P->d_ppmd, (void*)P->d_args, (void*)P->d_ext_bit, (void*)P->d_ppmd_byte})
+    if (q) cudaFree(q);
+  if (P->s_small) cudaStreamDestroy(P->s_small);
+  if (P->s_lstm) cudaStreamDestroy(P->s_lstm);
+  if (P->s_mix) cudaStreamDestroy(P->s_mix);
+  delete P;
+}
+
+int cmixb200_feed_external_bit(cmixb200_predictor* P, const uint16_t* codes) {
+  CK(cudaSetDevice(P->device));
+  CK(cudaMemcpy(P->d_ext_bit, codes, N_EXT * 2, cudaMemcpyHostToDevice));
+  P->ext_bit_valid = true;
+  return CMIXB200_OK;
+}
+int cmixb200_feed_external_byte(cmixb200_predictor* P, const float* ppmd256) {
+  CK(cudaSetDevice(P->device));
+  CK(cudaMemcpy(P->d_ppmd_byte, ppmd256, 256 * 4, cudaMemcpyHostToDevice));
+  P->ppmd_byte_valid = true;
+  return CMIXB200_OK;
+}
+
+float cmixb200_predict(cmixb200_predictor* P) {
+  const Tables T = g_tables.T;
+  if (cudaSetDevice(P->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1.0f; }
+  small_predict_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, T);
+  lstm_predict_kernel<<<1, 32, 0, P->s_mix>>>(P->d_st, T);
+  mix_predict_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T, P->ext_bit_valid ? P->d_ext_bit : nullptr);
+  P->launches += 3;
+  float p = -1.0f;
+  cudaError_t e = cudaMemcpyAsync(&p, &P->d_st->last_p, 4, cudaMemcpyDeviceToHost, P->s_mix);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);
+  if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
+  P->ext_bit_valid = false;
+  return p;
+}
+
+int cmixb200_perceive(cmixb200_predictor* P, int bit) {
+  CK(cudaSetDevice(P->device));
+  bit = bit ? 1 : 0;
+  const bool byte_done = P->bit_context >= 128;
+  const u32 full = (P->bit_context * 2 + bit) & 255;
+  const float* ppmd = (byte_done && P->ppmd_byte_valid) ? P->d_ppmd_byte : nullptr;
+  float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
+  small_perceive_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, bit, ppmd, 0);
+  mix_perceive_kernel<<<1, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
+  lstm_perceive_kernel<<<1, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, bit, byte_done ? 1 : 0, full, ppmd);
+  P->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(P->s_mix));
+  P->bits_done++;
+  P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
+  if (byte_done) P->ppmd_byte_valid = false;
+  return CMIXB200_OK;
+}
+
+int cmixb200_pretrain(cmixb200_predictor* P, int bit) {
+  CK(cudaSetDevice(P->device));
+  bit = bit ? 1 : 0;
+  const Tables T = g_tables.T;
+  const bool byte_done = P->bit_context >= 128;
+  small_predict_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, T);
+  small_perceive_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, bit, nullptr, 1);
+  P->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(P->s_mix));
+  P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
+  return CMIXB200_OK;
+}
+
+int cmixb200_code_bytes_device(cmixb200_predictor* P, const uint8_t* d_bytes, size_t n_bytes, const uint16_t* d_ext,
+                               const float* d_ppmd, float* d_p_out) {
+  return CodeDevice(P, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, false);
+}
+
+int cmixb200_code_bytes(cmixb200_predictor* P, const uint8_t* bytes, size_t n_bytes, const uint16_t* ext,
+                        const float* ppmd, float* p_out) {
+  CK(cudaSetDevice(P->device));
+  const size_t kSub = 4096;     // host staging granularity: 4096 B of input = 132 MB of replayed codes
+  if (P->stage_bytes < kSub) {
+    CK(cudaMalloc(&P->d_bytes, kSub));
+    CK(cudaMalloc(&P->d_ext, kSub * 8 * N_EXT * 2));
+    CK(cudaMalloc(&P->d_ppmd, kSub * 256 * 4));
+    P->stage_bytes = kSub;
+  }
+  for (size_t off = 0; off < n_bytes; off += kSub) {
+    const size_t n = n_bytes - off < kSub ? n_bytes - off : kSub;
+    CK(cudaMemcpy(P->d_bytes, bytes + off, n, cudaMemcpyHostToDevice));
+    if (ext) CK(cudaMemcpy(P->d_ext, ext + off * 8 * N_EXT, n * 8 * N_EXT * 2, cudaMemcpyHostToDevice));
+    if (ppmd) CK(cudaMemcpy(P->d_ppmd, ppmd + off * 256, n * 256 * 4, cudaMemcpyHostToDevice));
+    TRY(EnsureScratch(P, n));
+    TRY(CodeDevice(P, P->d_bytes, n, ext ? P->d_ext : nullptr, ppmd ? P->d_ppmd : nullptr, P->d_p, false));
+    CK(cudaMemcpy(p_out + off * 8, P->d_p, n * 8 * 4, cudaMemcpyDeviceToHost));
+  }
+  return CMIXB200_OK;
+}
+
+int cmixb200_pretrain_bytes(cmixb200_predictor* P, const uint8_t* bytes, size_t n_bytes) {
+  CK(cudaSetDevice(P->device));
+  u8* d = nullptr;
+  CK(cudaMalloc(&d, n_bytes ? n_bytes : 1));
+  CK(cudaMemcpy(d, bytes, n_bytes, cudaMemcpyHostToDevice));
+  int r = CodeDevice(P, d, n_bytes, nullptr, nullptr, nullptr, true);
+  cudaFree(d);
+  return r;
+}
+
+int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes, size_t n_bytes,
+                               const uint16_t* const* d_ext, const float* const* d_ppmd, float* const* d_p_out) {
+  if (n_streams <= 0 || n_bytes == 0) return CMIXB200_OK;
+  cmixb200_predictor* lead = preds[0];
+  CK(cudaSetDevice(lead->device));
+  std::vector<ChunkArgs> args(n_streams);
+  std::vector<float> decay;
+  for (int s = 0; s < n_streams; ++s) {
+    cmixb200_predictor* P = preds[s];
+    if (P->device != lead->device || P->bit_context != 1) { g_last_error = "batch: streams must share a device and be byte aligned"; return CMIXB200_ERR_ARG; }
+    TRY(EnsureScratch(P, n_bytes));
+    FillDecay(decay, P->bits_done, n_bytes * 8);
+    CK(cudaMemcpy(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
+    ChunkArgs& a = args[s];
+    memset(&a, 0, sizeof a);
+    a.st = P->d_st; a.bytes = d_bytes[s]; a.ext = d_ext ? d_ext[s] : nullptr; a.ppmd = d_ppmd ? d_ppmd[s] : nullptr;
+    a.decay = P->d_decay; a.small_x = P->d_small_x; a.sel = P->d_sel; a.lstm_x = P->d_lstm_x; a.p_out = d_p_out[s];
+    a.n_bytes = (u32)n_bytes;
+  }
+  ChunkArgs* d_args = nullptr;
+  CK(cudaMalloc(&d_args, sizeof(ChunkArgs) * n_streams));
+  CK(cudaMemcpy(d_args, args.data(), sizeof(ChunkArgs) * n_streams, cudaMemcpyHostToDevice));
+  int r = LaunchChunk(lead, d_args, n_streams, false);
+  if (r == CMIXB200_OK) {
+    cudaError_t e = cudaStreamSynchronize(lead->s_small);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lead->s_lstm);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lead->s_mix);
+    if (e != cudaSuccess) { g_last_error = std::string("batch: ") + cudaGetErrorString(e); r = CMIXB200_ERR_CUDA; }
+  }
+  cudaFree(d_args);
+  if (r == CMIXB200_OK) for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
+  return r;
+}
+
+unsigned long long cmixb200_kernel_launches(const cmixb200_predictor* P) { return P->launches; }
+void* cmixb200_mix_stream(cmixb200_predictor* P) { return (void*)P->s_mix; }
+
+int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t bytes) {
+  CK(cudaSetDevice(P->device));
+  const void* src = nullptr;
+  switch (what) {
+    case CMIXB200_DBG_SMALL_X: src = P->d_small_x; break;
+    case CMIXB200_DBG_SEL: src = P->d_sel; break;
+    case CMIXB200_DBG_LSTM_X: src = P->d_lstm_x; break;
+    case CMIXB200_DBG_LSTM_PROBS: src = &P->d_st->lstm.bm.probs[0]; break;
+    case CMIXB200_DBG_ERROR_FLAGS: src = &P->d_st->small.error; break;
+    default: g_last_error = "unknown debug id"; return CMIXB200_ERR_ARG;
+  }
+  CK(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+  return CMIXB200_OK;
+}
+
+}  // extern "C"

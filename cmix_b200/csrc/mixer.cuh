@@ -1,0 +1,490 @@
+// cmix_b200/csrc/mixer.cuh
+//
+// Kernel "mix": the three-layer gated logistic mixer + the integer SSE stage
+// (reference src/mixer/mixer.cpp:16-72, src/mixer/mixer-input.cpp,
+// src/predictor.cpp:388-418,432-437, src/mixer/sse.cpp).
+// This is the roofline-defining kernel: per coded bit it touches
+// 26*(2078+i) + 20*(29+i) + 49 = 55 172 fp32 weights twice (dot, then SGD).
+//
+// Layout: one thread-block CLUSTER of 2 CTAs per stream (persistent over the
+// whole chunk). CTA r keeps the currently selected weight rows of layer-0
+// mixers [13r, 13r+13) resident in shared memory (13 x 8.4 KB): a row is read
+// from HBM only when its selector context changes (16 of the 26 selectors
+// change once per byte, not per bit) and written back only when it is evicted,
+// so steady-state HBM traffic is well under the algorithmic 450 KB/bit.
+//
+// Parity contract: the reference sums each dot product sequentially in fp32
+// (mixer.cpp:41-43, no FMA). A tree/warp-shuffle reduction changes the rounding
+// and, through the 15-bit SSE quantisation (sse.cpp:321), moves the coded
+// probability by >1e-5 on a fraction of bits. So each dot product is ONE serial
+// FADD chain here, and the parallelism is ACROSS the 13 chains of a CTA (13
+// lanes of one warp, conflict-free row pitch in shared memory) and across the
+// 480 other threads that stage inputs, move rows and apply the SGD update.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "exact_math.h"
+#include "small_models.cuh"
+#include "state.h"
+
+namespace cmixb200 {
+namespace cg = cooperative_groups;
+
+enum {
+  MIX_THREADS = 512,
+  MIX_PER_CTA = 13,
+  ROW_PITCH_S = 2108,     // shared-memory row pitch: 527 float4 (odd) -> LDS.128 conflict-free across lanes
+};
+
+struct MixShared {
+  float rows[MIX_PER_CTA][ROW_PITCH_S];
+  float x[N_INPUTS + 26 + 8];     // staged inputs followed by the 26 layer-0 "extra inputs"
+  float mains[N_L0 + 6];          // main dot products of all 26 layer-0 mixers (CTA0 collects)
+  float we[N_L0][N_L0 + 2];       // extra-input weights of all 26 layer-0 mixers (CTA0 collects)
+  float upd[N_L0 + 6];            // SGD coefficient `update` per layer-0 mixer
+  u32 cur_slot[MIX_PER_CTA + 3];  // resident row per local mixer (0xffffffff = none)
+  u32 want_slot[MIX_PER_CTA + 3];
+  u32 shrink[MIX_PER_CTA + 3];
+  u32 sel[SEL_PITCH];
+  float in1[L1_IN + 3], in2[L2_IN + 3];
+  float l1row[N_L1][ROW_PITCH_L1];
+  float l2row[ROW_PITCH_L2];
+  float l1extra[N_L1 + 4];
+  float upd1[N_L1 + 4];
+  u32 slot1[N_L1 + 4];
+  u32 shrink1[N_L1 + 4];
+  float mixp[N_MIXERS + 1];
+  int bit;
+};
+
+// Mixer::GetContextData (mixer.cpp:16-36): first-come row assignment, overflow row after 10 000.
+__device__ __forceinline__ u32 resolve_slot(MixerState& m, u32 ctx) {
+  u32 s = m.slot_table[ctx];
+  if (s == 0) {
+    const u32 cap = m.n_rows - 1;                      // = min(table_size, 10000)
+    if (m.n_assigned < cap && m.n_assigned < (u32)SLOT_LIMIT) { s = ++m.n_assigned; m.slot_table[ctx] = s; }
+    else s = m.n_rows;                                 // shared overflow row (key 0xDEADBEEF)
+  }
+  return s - 1;
+}
+
+// `update` of Mixer::Perceive (mixer.cpp:58-66); also advances the step counters.
+__device__ __forceinline__ float mixer_update_coeff(MixerState& m, u32 slot, float decay_base, float p, int bit, u32* shrink) {
+  const u64 rs = m.row_steps[slot];
+  float decay = decay_base;
+  decay = (float)((double)decay * (1.5 - ((1.0 * (double)rs) / (double)m.max_steps)));
+  const float update = XM_FMUL(XM_FMUL(decay, m.lr), XM_FSUB(xm_logistic(p), (float)bit));
+  const u64 ns = rs + 1;
+  m.row_steps[slot] = ns;
+  if (ns > m.max_steps) m.max_steps = ns;
+  *shrink = ((ns & 1023) == 0) ? 1u : 0u;
+  return update;
+}
+
+__device__ __forceinline__ float clamp_stretched(const Tables& T, float p) {    // mixer-input.cpp:17-27
+  if (p > T.stretch_max) p = T.stretch_max; else if (p < T.stretch_min) p = T.stretch_min;
+  return p;
+}
+
+// ------------------------------------------------------------------ SSE ----
+__device__ __forceinline__ int sse_extrap(int p1, int C) {
+  p1 = (((p1 - 16384) * C) >> 13) + 16384;
+  if (p1 < 1) p1 = 1;
+  if (p1 > 32767) p1 = 32767;
+  return p1;
+}
+__device__ __forceinline__ int sse_rdiv(int x, int a, int d) { return x >= 0 ? (x + a) >> d : -((-x + a) >> d); }
+__device__ __forceinline__ int sse_mixup(int w, int s1, int s0) {
+  int x = s1 + sse_rdiv((w - 16384) * (s0 - s1), 1 << 14, 15);
+  return (x > 0) ? (x < 32768) ? x : 32767 : 1;
+}
+__device__ __forceinline__ int sse_mask1(int j) {   // M_mx1mask0 (sse.cpp:190)
+  if (j < 2) return 0;
+  if (j <= 32) return j - 1;
+  if (j <= 63) return 31 + (j - 32) / 2;
+  if (j <= 127) return 47 + (j - 64) / 4;
+  return 63 + (j - 128) / 8;
+}
+__device__ __forceinline__ int sse_pred(const u16* bucket, int iP, int* sw, int* q, int* P) {
+  *q = (6 * iP) >> 15;
+  *sw = (6 * iP) & 32767;
+  int f = (((32768 - *sw) * (int)bucket[*q] + *sw * (int)bucket[*q + 1]) >> 15) - 8192;
+  if (f <= 0) f = 1;
+  if (f >= 32768) f = 32767;
+  *P = f;
+  return f;
+}
+__device__ __forceinline__ void sse_bucket_update(u16* bucket, int c, int wr0, int sw, int q, int P) {
+  P = P * (32768 - wr0) >> 15;
+  if (c == 0) P += wr0;
+  const int dC = (int)bucket[q] - (int)bucket[q + 1];
+  const int sw_dC = (sw * dC + 32767) >> 15;
+  bucket[q] = (u16)(P + sw_dC + 8192);
+  bucket[q + 1] = (u16)(P - (dC - sw_dC) + 8192);
+}
+__device__ __forceinline__ void sse_mix_update(int* w, int y, int p0, int p1, int wq, int pm) {
+  const int py = 32768 - (y << 15);
+  const int e = py - pm;
+  int d = sse_rdiv(e * (p0 - p1), 1 << 14, 15);
+  d = sse_rdiv(d * wq, 1 << 14, 15);
+  *w += d;
+}
+// SSE::Predict (sse.cpp:320-324 -> M_Estimate :243-289). Single thread.
+__device__ float sse_predict(SseState& S, float input) {
+  const int discrete = (int)XM_FADD(1.0f, XM_FMUL(XM_FSUB(1.0f, input), 32766.0f));
+  const u32 p = (u32)discrete;
+  const u32 j = S.j, pc = S.pc, ffl = S.ffl, prq = p >> 11;
+  const u32 q3 = (prq > 0) + (prq > 14);
+  const u32 q4 = (prq > 0) + (prq > 7) + (prq > 14);
+  S.sm7x = ((((q3 << 5) + (ffl & 31)) << 8) + (pc & 255)) * 255 + (j < 2 ? 0 : j - 1);
+  S.mix2 = ((((q3 << 1) + (ffl & 1)) << 8) + (pc & 255)) * 256 + j;
+  S.sm6x = ((((q3 << 7) + (ffl & 127)) << 8) + (pc & 255)) * 256 + j;
+  S.mix1 = ((((q4 << 8) + (ffl & 255)) << 3) + ((pc >> 5) & 7)) * 79 + sse_mask1((int)j);
+  const u16* st = S.st; const u16* sq = S.sq;
+  const int stp = st[p];
+  const int p1 = sse_pred(S.s6 + (size_t)S.sm6x * 8, sq[sse_extrap(stp, 10240)], &S.sw6, &S.q6, &S.P6);
+  const int s0 = sse_extrap(stp, 7935);
+  const int s1 = sse_extrap(st[p1], 9592);
+  S.mix1_s0 = s0; S.mix1_s1 = s1;
+  int s2 = sse_mixup(S.x1[S.mix1], s0, s1);
+  s2 = sse_extrap(s2, 8092);
+  S.mix1_p = sq[s2];
+  const int p2 = sse_pred(S.s7 + (size_t)S.sm7x * 8, sq[sse_extrap(stp, 8200)], &S.sw7, &S.q7, &S.P7);
+  const int s4 = sse_extrap(st[p2], 7677);
+  S.mix2_s0 = s2; S.mix2_s1 = s4;
+  int s5 = sse_mixup(S.x2[S.mix2], s2, s4);
+  s5 = sse_extrap(s5, 8202);
+  S.mix2_p = sq[s5];
+  const int estimate = S.mix2_p;
+  return (float)(1.0 - ((double)(estimate - 1) / 32766.0));
+}
+// SSE::Perceive (M_Update, sse.cpp:291-305). Single thread.
+__device__ void sse_perceive(SseState& S, int bit) {
+  sse_bucket_update(S.s6 + (size_t)S.sm6x * 8, bit, 106, S.sw6, S.q6, S.P6);
+  sse_mix_update(&S.x1[S.mix1], bit, S.mix1_s0, S.mix1_s1, 6202, S.mix1_p);
+  sse_bucket_update(S.s7 + (size_t)S.sm7x * 8, bit, 127, S.sw7, S.q7, S.P7);
+  sse_mix_update(&S.x2[S.mix2], bit, S.mix2_s0, S.mix2_s1, 8320, S.mix2_p);
+  S.j += S.j + bit;
+  if (S.j >= 256) {
+    S.ffl = (u8)(S.ffl * 2 + (S.pc >= 0x40));
+    S.pc = (u8)S.j;
+    S.j = 1;
+  }
+}
+
+// --------------------------------------------------------- layer-0 chains --
+// 13 independent serial FADD chains, one per lane; weights in shared memory.
+__device__ __forceinline__ float chain_l0(const float* __restrict__ x, const float* __restrict__ row) {
+  float p = 0.0f;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* w4 = reinterpret_cast<const float4*>(row);
+#pragma unroll 8
+  for (int k = 0; k < N_INPUTS / 4; ++k) {            // 519 * 4 = 2076
+    const float4 a = x4[k], b = w4[k];
+    p = XM_FADD(p, XM_FMUL(a.x, b.x));
+    p = XM_FADD(p, XM_FMUL(a.y, b.y));
+    p = XM_FADD(p, XM_FMUL(a.z, b.z));
+    p = XM_FADD(p, XM_FMUL(a.w, b.w));
+  }
+  p = XM_FADD(p, XM_FMUL(x[2076], row[2076]));
+  p = XM_FADD(p, XM_FMUL(x[2077], row[2077]));
+  return p;
+}
+
+// Stage the 2078 layer-0 inputs of bit t into shared memory (predictor.cpp:362-387 order).
+__device__ __forceinline__ void stage_inputs(float* x, const Tables& T, const u16* ext, const float* small_x,
+                                             float lstm_x, int tid, int nthreads) {
+  for (int k = tid; k < N_INPUTS; k += nthreads) {
+    float v;
+    if (k < 3) v = small_x[k];
+    else if (k < 3 + N_EXT) {
+      const u32 code = ext ? ext[k - 3] : 0xFFFFu;
+      v = T.lut12[code == 0xFFFFu ? 4096 : code];
+    }
+    else if (k < 2076) v = small_x[k - N_EXT];
+    else if (k == 2076) v = small_x[N_SMALL];
+    else v = lstm_x;
+    x[k] = v;
+  }
+}
+
+// auxiliary_context_ (predictor.cpp:388-393)
+__device__ __forceinline__ u32 aux_context(const float* x) {
+  float avg = 0.0f;
+  avg = XM_FADD(avg, xm_logistic(x[433]));
+  avg = XM_FADD(avg, xm_logistic(x[2024]));
+  avg = XM_FADD(avg, xm_logistic(x[2077]));
+  avg = XM_FDIV(avg, 3.0f);
+  return (u32)(unsigned long long)XM_FMUL(avg, 15.0f);
+}
+
+// Layers 1 and 2 + SSE for one bit, run by ONE warp. Inputs: sh.mains (26 layer-0 main sums),
+// sh.we (their extra weights), sh.l1row/sh.l2row (selected rows). Outputs: sh.x[2078..] extras,
+// sh.mixp, sh.in1, sh.in2, sh.l1extra; returns the final probability in lane 0.
+__device__ float final_stage(MixShared& sh, const Tables& T, SseState& sse, int lane) {
+  // ---- layer 0: forward substitution through the "extra inputs" (mixer.cpp:45-53) ----
+  float main = lane < N_L0 ? sh.mains[lane] : 0.0f;
+  float e = 0.0f, pfin = 0.0f;
+  for (int k = 0; k < N_L0; ++k) {
+    if (lane == k) pfin = XM_FADD(main, e);
+    const float pk = __shfl_sync(0xffffffffu, pfin, k);
+    const float ck = clamp_stretched(T, pk);
+    if (lane == k) { sh.mixp[k] = pk; sh.x[N_INPUTS + k] = ck; sh.in1[k] = ck; sh.in2[k] = ck; }
+    if (lane > k && lane < N_L0) e = XM_FADD(e, XM_FMUL(ck, sh.we[lane][k]));
+  }
+  if (lane < N_AUX) {
+    const int idx = lane == 0 ? 433 : (lane == 1 ? 2024 : 2077);
+    const float c = clamp_stretched(T, sh.x[idx]);
+    sh.in1[N_L0 + lane] = c;
+    sh.in2[N_L0 + N_L1 + lane] = c;
+  }
+  __syncwarp();
+  // ---- layer 1 ----
+  main = 0.0f;
+  if (lane < N_L1) {
+    const float* w = sh.l1row[lane];
+#pragma unroll
+    for (int k = 0; k < L1_IN; ++k) main = XM_FADD(main, XM_FMUL(sh.in1[k], w[k]));
+  }
+  e = 0.0f; pfin = 0.0f;
+  for (int k = 0; k < N_L1; ++k) {
+    if (lane == k) pfin = XM_FADD(main, e);
+    const float pk = __shfl_sync(0xffffffffu, pfin, k);
+    const float ck = clamp_stretched(T, pk);
+    if (lane == k) { sh.mixp[N_L0 + k] = pk; sh.l1extra[k] = ck; sh.in2[N_L0 + k] = ck; }
+    if (lane > k && lane < N_L1) e = XM_FADD(e, XM_FMUL(ck, sh.l1row[lane][L1_IN + k]));
+  }
+  __syncwarp();
+  // ---- layer 2 + squash + SSE ----
+  float p = 0.0f;
+  if (lane == 0) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < L2_IN; ++k) s = XM_FADD(s, XM_FMUL(sh.in2[k], sh.l2row[k]));
+    s = XM_FADD(s, 0.0f);                                // p_ += e with no extra inputs
+    sh.mixp[N_L0 + N_L1] = s;
+    p = sse_predict(sse, xm_logistic(s));
+  }
+  return p;
+}
+
+// Bulk kernel: cluster of 2 CTAs per stream.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MIX_THREADS, 1)
+mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const ChunkArgs a = args_all[blockIdx.x / 2];
+  StreamState* st = a.st;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MixShared& sh = *reinterpret_cast<MixShared*>(smem_raw);
+  MixShared* sh0 = cluster.map_shared_rank(&sh, 0);     // CTA 0's shared memory (DSMEM)
+  MixShared* sh1 = cluster.map_shared_rank(&sh, 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = rank * MIX_PER_CTA;                     // first layer-0 mixer owned by this CTA
+
+  if (tid < MIX_PER_CTA) sh.cur_slot[tid] = 0xffffffffu;
+  __syncthreads();
+
+  const u64 n_bits = (u64)a.n_bytes * 8;
+  for (u64 t = 0; t < n_bits; ++t) {
+    const int bit = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
+    // ---------------- B0: stage inputs, resolve rows, make them resident ----------------
+    stage_inputs(sh.x, T, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], tid, MIX_THREADS);
+    if (tid < SEL_PITCH) sh.sel[tid] = tid < N_MIXERS ? a.sel[t * SEL_PITCH + tid] : 0;
+    __syncthreads();
+    if (tid == 0) sh.sel[12] = aux_context(sh.x);        // layer-0 mixer 12 is selected by auxiliary_context_
+    __syncthreads();
+    if (tid < MIX_PER_CTA) {
+      MixerState& m = st->mixer[m0 + tid];
+      sh.want_slot[tid] = resolve_slot(m, sh.sel[m0 + tid]);
+    } else if (rank == 0 && tid >= 32 && tid < 32 + N_L1 + 1) {
+      const int i = tid - 32;                            // layer-1 mixers 0..19, then the layer-2 mixer
+      MixerState& m = st->mixer[N_L0 + i];
+      sh.slot1[i] = resolve_slot(m, sh.sel[N_L0 + i]);
+    }
+    __syncthreads();
+    for (int i = 0; i < MIX_PER_CTA; ++i) {              // evict + load rows whose selector moved
+      const u32 want = sh.want_slot[i], cur = sh.cur_slot[i];
+      if (want != cur) {
+        MixerState& m = st->mixer[m0 + i];
+        float4* srow = reinterpret_cast<float4*>(sh.rows[i]);
+        if (cur != 0xffffffffu) {
+          float4* g = reinterpret_cast<float4*>(m.rows + (size_t)cur * ROW_PITCH_L0);
+          for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) g[k] = srow[k];
+        }
+        const float4* g = reinterpret_cast<const float4*>(m.rows + (size_t)want * ROW_PITCH_L0);
+        for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) srow[k] = g[k];
+      }
+    }
+    if (rank == 0) {                                     // layer-1/2 rows are tiny: fetch every bit
+      for (int k = tid; k < N_L1 * ROW_PITCH_L1; k += MIX_THREADS) {
+        const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
+        sh.l1row[i][c] = st->mixer[N_L0 + i].rows[(size_t)sh.slot1[i] * ROW_PITCH_L1 + c];
+      }
+      if (tid < ROW_PITCH_L2) sh.l2row[tid] = st->mixer[N_L0 + N_L1].rows[(size_t)sh.slot1[N_L1] * ROW_PITCH_L2 + tid];
+    }
+    __syncthreads();
+    if (tid < MIX_PER_CTA) sh.cur_slot[tid] = sh.want_slot[tid];
+    // ---------------- B1: the 13 serial dot-product chains of this CTA ----------------
+    if (warp == 0) {
+      if (lane < MIX_PER_CTA) {
+        const float p = chain_l0(sh.x, sh.rows[lane]);
+        sh0->mains[m0 + lane] = p;                       // DSMEM store into CTA 0
+      }
+    } else {
+      // meanwhile: publish this CTA's extra-input weights to CTA 0
+      for (int k = tid - 32; k < MIX_PER_CTA * N_L0; k += MIX_THREADS - 32) {
+        const int i = k / N_L0, c = k - i * N_L0;
+        sh0->we[m0 + i][c] = sh.rows[i][N_INPUTS + c];
+      }
+    }
+    cluster.sync();
+    // ---------------- B2: CTA 0 finishes the network and computes the SGD coefficients ----------------
+    if (rank == 0 && warp == 0) {
+      const float p = final_stage(sh, T, st->sse, lane);
+      if (lane == 0) {
+        const float ov = a.lstm_x[2 * t + 1];
+        a.p_out[t] = ov >= 0.0f ? ov : p;                // vocabulary override (predictor.cpp:415-417)
+      }
+      __syncwarp();
+      const float decay = a.decay[t];
+      if (lane < N_L0) {
+        u32 shr;
+        const float u = mixer_update_coeff(st->mixer[lane], lane < MIX_PER_CTA ? sh.cur_slot[lane] : sh1->cur_slot[lane - MIX_PER_CTA],
+                                           decay, sh.mixp[lane], bit, &shr);
+        sh.upd[lane] = u; sh1->upd[lane] = u;
+        if (lane < MIX_PER_CTA) sh.shrink[lane] = shr; else sh1->shrink[lane - MIX_PER_CTA] = shr;
+        sh1->x[N_INPUTS + lane] = sh.x[N_INPUTS + lane];   // the 26 extra inputs
+      }
+      if (lane < N_L1 + 1) {
+        u32 shr;
+        const int mi = N_L0 + lane;
+        sh.upd1[lane] = mixer_update_coeff(st->mixer[mi], sh.slot1[lane], decay, sh.mixp[mi], bit, &shr);
+        sh.shrink1[lane] = shr;
+      }
+      if (lane == 0) sse_perceive(st->sse, bit);
+    }
+    cluster.sync();
+    // ---------------- B3: SGD on the resident rows (mixer.cpp:66-71) ----------------
+    for (int i = 0; i < MIX_PER_CTA; ++i) {
+      const float u = sh.upd[m0 + i];
+      const bool shr = sh.shrink[i] != 0;
+      float* row = sh.rows[i];
+      const int n = N_INPUTS + m0 + i;
+      for (int k = tid; k < n; k += MIX_THREADS) {
+        float w = XM_FSUB(row[k], XM_FMUL(u, sh.x[k]));
+        if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+        row[k] = w;
+      }
+    }
+    if (rank == 0) {
+      for (int k = tid; k < (N_L1 + 1) * ROW_PITCH_L1; k += MIX_THREADS) {
+        const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
+        float w, xin; int n;
+        if (i < N_L1) { n = L1_IN + i; w = sh.l1row[i][c]; xin = c < L1_IN ? sh.in1[c] : sh.l1extra[c - L1_IN]; }
+        else { n = L2_IN; w = sh.l2row[c]; xin = sh.in2[c]; }
+        if (c < n) {
+          w = XM_FSUB(w, XM_FMUL(sh.upd1[i], xin));
+          if (sh.shrink1[i]) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+          st->mixer[N_L0 + i].rows[(size_t)sh.slot1[i] * ROW_PITCH_L1 + c] = w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // flush resident rows so that HBM holds the complete state between launches
+  for (int i = 0; i < MIX_PER_CTA; ++i) {
+    const u32 cur = sh.cur_slot[i];
+    if (cur != 0xffffffffu) {
+      float4* g = reinterpret_cast<float4*>(st->mixer[m0 + i].rows + (size_t)cur * ROW_PITCH_L0);
+      const float4* srow = reinterpret_cast<const float4*>(sh.rows[i]);
+      for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) g[k] = srow[k];
+    }
+  }
+  if (rank == 0 && tid == 0) st->bits_done += n_bits;
+  cluster.sync();
+}
+
+}  // namespace cmixb200
+
+// ---------------------------------------------------------------------------
+// Lock-step halves (host calls Predictor::Predict / Perceive bit by bit, e.g. the
+// reference's Decoder, coder/decoder.cpp:20-39). Single CTA, rows stay in HBM.
+// Same arithmetic as mix_kernel; intermediate vectors are parked in StreamState.
+namespace cmixb200 {
+
+__global__ void __launch_bounds__(MIX_THREADS, 1)
+mix_predict_kernel(StreamState* st, Tables T, const u16* ext /* device, N_EXT codes or null */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MixShared& sh = *reinterpret_cast<MixShared*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_inputs(sh.x, T, ext, st->small_x, st->lstm_x, tid, MIX_THREADS);
+  if (tid < SEL_PITCH) sh.sel[tid] = tid < N_MIXERS ? st->sel[tid] : 0;
+  __syncthreads();
+  if (tid == 0) sh.sel[12] = aux_context(sh.x);
+  __syncthreads();
+  if (tid < N_MIXERS) { const u32 s = resolve_slot(st->mixer[tid], sh.sel[tid]); st->slot[tid] = s; if (tid >= N_L0) sh.slot1[tid - N_L0] = s; }
+  __syncthreads();
+  for (int k = tid; k < N_L1 * ROW_PITCH_L1; k += MIX_THREADS) {
+    const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
+    sh.l1row[i][c] = st->mixer[N_L0 + i].rows[(size_t)sh.slot1[i] * ROW_PITCH_L1 + c];
+  }
+  if (tid < ROW_PITCH_L2) sh.l2row[tid] = st->mixer[N_L0 + N_L1].rows[(size_t)sh.slot1[N_L1] * ROW_PITCH_L2 + tid];
+  for (int k = tid; k < N_L0 * N_L0; k += MIX_THREADS) {
+    const int i = k / N_L0, c = k - i * N_L0;
+    sh.we[i][c] = st->mixer[i].rows[(size_t)st->slot[i] * ROW_PITCH_L0 + N_INPUTS + c];
+  }
+  if (warp == 0 && lane < N_L0)
+    sh.mains[lane] = chain_l0(sh.x, st->mixer[lane].rows + (size_t)st->slot[lane] * ROW_PITCH_L0);
+  __syncthreads();
+  if (warp == 0) {
+    const float p = final_stage(sh, T, st->sse, lane);
+    if (lane == 0) st->last_p = st->lstm_override >= 0.0f ? st->lstm_override : p;
+  }
+  __syncthreads();
+  for (int k = tid; k < N_INPUTS; k += MIX_THREADS) st->x[k] = sh.x[k];
+  if (tid < N_L0) st->extras0[tid] = sh.x[N_INPUTS + tid];
+  if (tid < N_L1) st->extras1[tid] = sh.l1extra[tid];
+  if (tid < L2_IN) st->in2[tid] = sh.in2[tid];
+  if (tid < N_MIXERS) st->mix_p[tid] = sh.mixp[tid];
+}
+
+__global__ void __launch_bounds__(MIX_THREADS, 1)
+mix_perceive_kernel(StreamState* st, int bit, float decay_base) {
+  __shared__ float upd[N_MIXERS + 1];
+  __shared__ u32 shrink[N_MIXERS + 1];
+  const int tid = threadIdx.x;
+  if (tid < N_MIXERS) upd[tid] = mixer_update_coeff(st->mixer[tid], st->slot[tid], decay_base, st->mix_p[tid], bit, &shrink[tid]);
+  if (tid == 64) sse_perceive(st->sse, bit);
+  __syncthreads();
+  for (int i = 0; i < N_L0; ++i) {
+    float* row = st->mixer[i].rows + (size_t)st->slot[i] * ROW_PITCH_L0;
+    const int n = N_INPUTS + i;
+    for (int k = tid; k < n; k += MIX_THREADS) {
+      const float xin = k < N_INPUTS ? st->x[k] : st->extras0[k - N_INPUTS];
+      float w = XM_FSUB(row[k], XM_FMUL(upd[i], xin));
+      if (shrink[i]) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+      row[k] = w;
+    }
+  }
+  for (int k = tid; k < (N_L1 + 1) * ROW_PITCH_L1; k += MIX_THREADS) {
+    const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
+    const int mi = N_L0 + i;
+    const int n = i < N_L1 ? L1_IN + i : L2_IN;
+    if (c < n) {
+      float xin;
+      if (i < N_L1) {
+        if (c < N_L0) xin = st->extras0[c];                       // layer-1 input c = clamp(layer-0 output c)
+        else if (c < L1_IN) xin = st->in2[N_L0 + N_L1 + (c - N_L0)];   // the 3 auxiliary inputs
+        else xin = st->extras1[c - L1_IN];
+      } else xin = st->in2[c];
+      float* w = st->mixer[mi].rows + (size_t)st->slot[mi] * ROW_PITCH_L1 + c;
+      float v = XM_FSUB(*w, XM_FMUL(upd[mi], xin));
+      if (shrink[mi]) v = XM_FMUL(v, 1.0f - 3.0e-6f);
+      *w = v;
+    }
+  }
+  if (tid == 0) st->bits_done += 1;
+}
+
+}  // namespace cmixb200

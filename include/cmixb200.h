@@ -1,0 +1,83 @@
+/* include/cmixb200.h — C-ABI of the B200-native cmix predictor.
+ *
+ * Drop-in boundary: the reference's `class Predictor` (reference
+ * src/predictor.h:17-53), the only interface the reference's arithmetic coder
+ * (src/coder/encoder.cpp:15,23, src/coder/decoder.cpp:21,31), its runner
+ * (src/runner.cpp:205,246) and its pretrainer (src/preprocess/preprocessor.cpp:52,66)
+ * use. cmix_b200/shim/predictor.{h,cpp} re-declares that class with the same
+ * signature on top of these entry points.
+ *
+ * Plain pointers and sizes only; no C++ or torch types. All functions return
+ * CMIXB200_OK (0) or an error code; cmixb200_last_error() describes the failure.
+ * There is no CPU fallback behind any of them: without a usable sm_100 device
+ * they fail with CMIXB200_ERR_CUDA.
+ */
+#ifndef CMIXB200_H
+#define CMIXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { CMIXB200_OK = 0, CMIXB200_ERR_CUDA = 1, CMIXB200_ERR_ARG = 2 };
+
+enum {
+  CMIXB200_N_EXT = 2022,  /* replayed FXCM (431) + PAQ8 (1591) outputs per bit, as 12-bit codes k
+                             meaning k/4095 (paq8.cpp:497-500, fxcmv1.cpp:97-101); 0xFFFF = 0.5 */
+};
+
+typedef struct cmixb200_predictor cmixb200_predictor;
+
+/* Predictor::Predictor(const std::vector<bool>& vocab) (predictor.cpp:24-37) plus the
+ * `char* dictionary_path` side channel of runner.cpp:17 (may be NULL). `device` = CUDA ordinal. */
+int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int device,
+                    cmixb200_predictor** out);
+void cmixb200_destroy(cmixb200_predictor*);
+
+/* float Predictor::Predict() (predictor.cpp:361). Returns -1 on failure. */
+float cmixb200_predict(cmixb200_predictor*);
+/* void Predictor::Perceive(int bit) (predictor.cpp:421). */
+int cmixb200_perceive(cmixb200_predictor*, int bit);
+/* void Predictor::Pretrain(int bit) (predictor.cpp:471). */
+int cmixb200_pretrain(cmixb200_predictor*, int bit);
+
+/* Model groups that are not yet device resident (PAQ8, FXCM, PPMD) enter
+ * as replayed streams. Lock-step: feed the codes for the NEXT Predict(), and the 256-entry PPMD
+ * byte distribution (ppmd.cpp:1328-1338) for the byte the next Perceive() calls complete.
+ * Without them those inputs carry p = 0.5 / a flat distribution. */
+int cmixb200_feed_external_bit(cmixb200_predictor*, const uint16_t codes[CMIXB200_N_EXT]);
+int cmixb200_feed_external_byte(cmixb200_predictor*, const float ppmd[256]);
+
+/* Bulk compress-direction path: the n_bytes*8 Predict()/Perceive() pairs of runner.cpp:101-119
+ * (Compress) in one call; p_out receives the value Predict() returned before each bit.
+ * HOST buffers (copies are part of the call). ext: [n_bytes*8][2022] or NULL; ppmd: [n_bytes][256] or NULL. */
+int cmixb200_code_bytes(cmixb200_predictor*, const uint8_t* bytes, size_t n_bytes, const uint16_t* ext,
+                        const float* ppmd, float* p_out);
+/* Same with every buffer already in device memory. */
+int cmixb200_code_bytes_device(cmixb200_predictor*, const uint8_t* d_bytes, size_t n_bytes,
+                               const uint16_t* d_ext, const float* d_ppmd, float* d_p_out);
+/* n_streams independent predictors (independent files) advanced together in one launch set. */
+int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes,
+                               size_t n_bytes, const uint16_t* const* d_ext, const float* const* d_ppmd,
+                               float* const* d_p_out);
+/* preprocessor::Pretrain's loop (preprocessor.cpp:37-69) over a byte buffer (HOST). */
+int cmixb200_pretrain_bytes(cmixb200_predictor*, const uint8_t* bytes, size_t n_bytes);
+
+const char* cmixb200_last_error(void);
+/* kernels launched by this predictor so far (bench.py's gpu_launches). */
+unsigned long long cmixb200_kernel_launches(const cmixb200_predictor*);
+/* the cudaStream_t the mixer kernel runs on (for CUDA-event timing in bench.py). */
+void* cmixb200_mix_stream(cmixb200_predictor*);
+
+/* test hooks: copy intermediate arrays of the last bulk call to the host */
+enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, CMIXB200_DBG_LSTM_PROBS = 4,
+       CMIXB200_DBG_ERROR_FLAGS = 5 };
+int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
