@@ -265,6 +265,7 @@ struct cmixb200_predictor {
   u16* d_ext_bit = nullptr; bool ext_bit_valid = false;
   float* d_ppmd_byte = nullptr; bool ppmd_byte_valid = false;
   unsigned long long launches = 0;
+  unsigned long long* d_prof = nullptr;
   u8 vocab[256];
   int V = 0;
 
@@ -497,7 +498,7 @@ int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u
   memset(&a, 0, sizeof a);
   a.st = P->d_st; a.bytes = d_bytes; a.ext = d_ext; a.ppmd = d_ppmd; a.decay = P->d_decay;
   a.small_x = P->d_small_x; a.sel = P->d_sel; a.lstm_x = P->d_lstm_x; a.p_out = d_p_out;
-  a.n_bytes = (u32)n_bytes; a.pretrain = pretrain ? 1 : 0;
+  a.n_bytes = (u32)n_bytes; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
   if (!pretrain) {
     std::vector<float> decay;
     FillDecay(decay, P->bits_done, n_bytes * 8);
@@ -700,6 +701,9 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
     case CMIXB200_DBG_LSTM_X: src = P->d_lstm_x; break;
     case CMIXB200_DBG_LSTM_PROBS: src = &P->d_st->lstm.bm.probs[0]; break;
     case CMIXB200_DBG_ERROR_FLAGS: src = &P->d_st->small.error; break;
+    case CMIXB200_DBG_PROFILE:
+      if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 32 * 8)); CK(cudaMemset(P->d_prof, 0, 32 * 8)); }
+      src = P->d_prof; break;
     default: g_last_error = "unknown debug id"; return CMIXB200_ERR_ARG;
   }
   CK(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));

@@ -268,6 +268,8 @@ __device__ float final_stage(MixShared& sh, const Tables& T, SseState& sse, int 
   return p;
 }
 
+#define MIX_PROF(slot) do { if (prof_on) { const long long now_ = clock64(); a.prof[slot] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
+
 // Bulk kernel: cluster of 2 CTAs per stream.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MIX_THREADS, 1)
 mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
@@ -286,12 +288,15 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
   __syncthreads();
 
   const u64 n_bits = (u64)a.n_bytes * 8;
+  const bool prof_on = a.prof != nullptr && rank == 0 && tid == 0;
+  long long tprev = clock64();
   for (u64 t = 0; t < n_bits; ++t) {
     const int bit = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
     // ---------------- B0: stage inputs, resolve rows, make them resident ----------------
     stage_inputs(sh.x, T, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], tid, MIX_THREADS);
     if (tid < SEL_PITCH) sh.sel[tid] = tid < N_MIXERS ? a.sel[t * SEL_PITCH + tid] : 0;
     __syncthreads();
+    MIX_PROF(0);
     if (tid == 0) sh.sel[12] = aux_context(sh.x);        // layer-0 mixer 12 is selected by auxiliary_context_
     __syncthreads();
     if (tid < MIX_PER_CTA) {
@@ -303,6 +308,7 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
       sh.slot1[i] = resolve_slot(m, sh.sel[N_L0 + i]);
     }
     __syncthreads();
+    MIX_PROF(1);
     for (int i = 0; i < MIX_PER_CTA; ++i) {              // evict + load rows whose selector moved
       const u32 want = sh.want_slot[i], cur = sh.cur_slot[i];
       if (want != cur) {
@@ -324,6 +330,7 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
       if (tid < ROW_PITCH_L2) sh.l2row[tid] = st->mixer[N_L0 + N_L1].rows[(size_t)sh.slot1[N_L1] * ROW_PITCH_L2 + tid];
     }
     __syncthreads();
+    MIX_PROF(2);
     if (tid < MIX_PER_CTA) sh.cur_slot[tid] = sh.want_slot[tid];
     // ---------------- B1: the 13 serial dot-product chains of this CTA ----------------
     if (warp == 0) {
@@ -338,7 +345,9 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
         sh0->we[m0 + i][c] = sh.rows[i][N_INPUTS + c];
       }
     }
+    MIX_PROF(3);
     cluster.sync();
+    MIX_PROF(4);
     // ---------------- B2: CTA 0 finishes the network and computes the SGD coefficients ----------------
     if (rank == 0 && warp == 0) {
       const float p = final_stage(sh, T, st->sse, lane);
@@ -364,7 +373,9 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
       }
       if (lane == 0) sse_perceive(st->sse, bit);
     }
+    MIX_PROF(5);
     cluster.sync();
+    MIX_PROF(6);
     // ---------------- B3: SGD on the resident rows (mixer.cpp:66-71) ----------------
     for (int i = 0; i < MIX_PER_CTA; ++i) {
       const float u = sh.upd[m0 + i];
@@ -391,6 +402,7 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
       }
     }
     __syncthreads();
+    MIX_PROF(7);
   }
   // flush resident rows so that HBM holds the complete state between launches
   for (int i = 0; i < MIX_PER_CTA; ++i) {

@@ -166,6 +166,7 @@ struct ChunkArgs {
   float* p_out;                 // [n_bytes*8] result
   u32 n_bytes;
   u32 pretrain;                 // 1: Pretrain() semantics (models + contexts only)
+  unsigned long long* prof;     // optional [32] per-phase SM-cycle accumulators (null = off)
 };
 
 }  // namespace cmixb200
