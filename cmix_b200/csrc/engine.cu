@@ -27,6 +27,7 @@
 #include "exact_math.h"
 #include "lstm.cuh"
 #include "mixer.cuh"
+#include "mixer_v2.cuh"
 #include "small_models.cuh"
 #include "state.h"
 
@@ -238,6 +239,7 @@ int BuildSharedTables(int device) {
   CK(cudaMemcpyToSymbol(c_ivmap, ivmap, sizeof ivmap));
   CK(cudaMemcpyToSymbol(c_mixer_sel, msel, sizeof msel));
   CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
+  CK(cudaFuncSetAttribute(mix_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared2)));
   CK(cudaFuncSetAttribute(mix_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   CK(cudaFuncSetAttribute(lstm_perceive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
@@ -254,7 +256,7 @@ struct cmixb200_predictor {
   StreamState h;                       // host mirror of the pointer/parameter fields
   std::vector<void*> allocs;
   cudaStream_t s_small = nullptr, s_lstm = nullptr, s_mix = nullptr;
-  ChunkArgs* d_args = nullptr;
+  ChunkArgs* d_args = nullptr; size_t n_args = 0;
   // chunk scratch
   size_t scratch_bits = 0;
   float* d_small_x = nullptr; u32* d_sel = nullptr; float* d_lstm_x = nullptr; float* d_decay = nullptr; float* d_p = nullptr;
@@ -479,7 +481,9 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
     CK(cudaEventRecord(e2, lead->s_lstm));
     CK(cudaStreamWaitEvent(lead->s_mix, e1, 0));
     CK(cudaStreamWaitEvent(lead->s_mix, e2, 0));
-    mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
+    static const bool use_v1 = getenv("CMIXB200_MIX_V1") != nullptr;   // barrier-per-phase reference version of the kernel
+    if (use_v1) mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
+    else mix_kernel_v2<<<2 * n_streams, MIX_THREADS, sizeof(MixShared2), lead->s_mix>>>(d_args, T);
     lead->launches++;
     CK(cudaEventDestroy(e1));
     CK(cudaEventDestroy(e2));
@@ -494,19 +498,37 @@ int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u
   if (P->bit_context != 1) { g_last_error = "bulk coding must start on a byte boundary"; return CMIXB200_ERR_ARG; }
   CK(cudaSetDevice(P->device));
   TRY(EnsureScratch(P, n_bytes));
-  ChunkArgs a;
-  memset(&a, 0, sizeof a);
-  a.st = P->d_st; a.bytes = d_bytes; a.ext = d_ext; a.ppmd = d_ppmd; a.decay = P->d_decay;
-  a.small_x = P->d_small_x; a.sel = P->d_sel; a.lstm_x = P->d_lstm_x; a.p_out = d_p_out;
-  a.n_bytes = (u32)n_bytes; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
   if (!pretrain) {
     std::vector<float> decay;
     FillDecay(decay, P->bits_done, n_bytes * 8);
     CK(cudaMemcpyAsync(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice, P->s_mix));
     CK(cudaStreamSynchronize(P->s_mix));
   }
-  CK(cudaMemcpy(P->d_args, &a, sizeof a, cudaMemcpyHostToDevice));
-  TRY(LaunchChunk(P, P->d_args, 1, pretrain));
+  // Software pipeline over sub-chunks: the two producer kernels (small models, LSTM) of sub-chunk
+  // k+1 run on their own streams while the mixer consumes sub-chunk k.
+  static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 512;
+  const size_t n_sub = pretrain ? 1 : (n_bytes + kSub - 1) / kSub;
+  std::vector<ChunkArgs> args(n_sub);
+  for (size_t k = 0; k < n_sub; ++k) {
+    const size_t off = pretrain ? 0 : k * kSub;
+    const size_t n = pretrain ? n_bytes : (n_bytes - off < kSub ? n_bytes - off : kSub);
+    ChunkArgs& a = args[k];
+    memset(&a, 0, sizeof a);
+    a.st = P->d_st; a.bytes = d_bytes + off;
+    a.ext = d_ext ? d_ext + off * 8 * N_EXT : nullptr;
+    a.ppmd = d_ppmd ? d_ppmd + off * 256 : nullptr;
+    a.decay = P->d_decay + off * 8;
+    a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
+    a.lstm_x = P->d_lstm_x + off * 8 * 2; a.p_out = d_p_out ? d_p_out + off * 8 : nullptr;
+    a.n_bytes = (u32)n; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
+  }
+  if (P->n_args < n_sub) {
+    if (P->d_args) cudaFree(P->d_args);
+    CK(cudaMalloc(&P->d_args, sizeof(ChunkArgs) * n_sub));
+    P->n_args = n_sub;
+  }
+  CK(cudaMemcpy(P->d_args, args.data(), sizeof(ChunkArgs) * n_sub, cudaMemcpyHostToDevice));
+  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(P, P->d_args + k, 1, pretrain));
   CK(cudaStreamSynchronize(P->s_small));
   if (!pretrain) { CK(cudaStreamSynchronize(P->s_lstm)); CK(cudaStreamSynchronize(P->s_mix)); P->bits_done += n_bytes * 8; }
   return CMIXB200_OK;
@@ -535,7 +557,7 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
     cudaStreamCreateWithFlags(&P->s_small, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&P->s_lstm, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&P->s_mix, cudaStreamNonBlocking);
-    if (cudaMalloc(&P->d_args, sizeof(ChunkArgs)) != cudaSuccess || cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
+    if (cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
         cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
   }
   if (r != CMIXB200_OK) { cmixb200_destroy(P); return r; }

@@ -1,0 +1,577 @@
+// cmix_b200/csrc/mixer_v2.cuh
+//
+// Kernel "mix" v2: warp-specialised, barrier-free-across-CTAs version of the
+// gated mixer (same arithmetic as mixer.cuh, which documents the parity rules
+// and remains the lock-step / reference implementation).
+//
+// Critical recurrence per bit (layer 0 only):
+//     13 serial dot-product chains -> forward substitution through the extra
+//     inputs -> SGD coefficient -> weight update -> next bit's chains.
+// Everything else is taken off that path:
+//   * C warp   (warp 0)      : chains, extra-input substitution, coefficients.
+//   * M warps  (warps 1..14) : while the chains of bit t run they stage the
+//                              inputs of bit t+1, resolve its weight rows and
+//                              PREFETCH rows whose selector changes into spare
+//                              shared-memory buffers (bit-level selectors get a
+//                              second buffer); afterwards they apply the SGD
+//                              update of bit t and swap buffers.
+//   * T warp   (warp 15, CTA0): layers 1 and 2, the SSE stage and p_out, one
+//                              bit behind, fed through a 4-deep ring.
+// CTA 0 never waits for CTA 1: mixers 0..12 only need their own outputs as extra
+// inputs. CTA 1 receives the 13 clamped outputs of CTA 0 through DSMEM + a
+// sequence flag and trails by the flight time of that message.
+#pragma once
+#include "mixer.cuh"
+
+namespace cmixb200 {
+
+// Warp roles. The SM's 4 schedulers own warps (w % 4); the arbiter prefers the highest warp id,
+// so the latency-critical chain warp is the LAST warp and no mover shares its scheduler
+// (warps 3, 7, 11 stay parked at the final barrier).
+enum { V2_NBUF = 20, V2_RING = 4, V2_M_WARPS = 11, V2_M_THREADS = V2_M_WARPS * 32, V2_CM_THREADS = V2_M_THREADS + 32,
+       V2_C_WARP = 15, V2_T_WARP = 14 };
+
+struct RowJob { int buf; int mixer; u32 load_slot; u32 evict_slot; int do_evict; int do_load; };
+
+struct MixShared2 {
+  alignas(16) float rows[V2_NBUF][ROW_PITCH_S];
+  alignas(16) float x[2][N_INPUTS + 2];
+  int buf_cur[MIX_PER_CTA + 3], buf_alt[MIX_PER_CTA + 3];
+  u32 tag[V2_NBUF]; u32 dirty[V2_NBUF]; u64 steps[V2_NBUF];
+  u64 max_steps[MIX_PER_CTA + 3];
+  u32 want[MIX_PER_CTA + 3]; u32 swap_needed[MIX_PER_CTA + 3]; u32 late[MIX_PER_CTA + 3];
+  RowJob jobs[2 * MIX_PER_CTA]; int n_jobs;
+  float upd[MIX_PER_CTA + 3]; u32 shrink[MIX_PER_CTA + 3];
+  float extras[2][N_L0 + 6];                 // clamped layer-0 outputs of bit parity (update snapshot)
+  u32 sel[2][SEL_PITCH];
+  // CTA1 only: clamped outputs of mixers 0..12 received from CTA0
+  float ring_in[V2_RING][16]; volatile u32 ring_in_seq[V2_RING];
+  volatile u32 peer_progress;                // CTA0 only: bits CTA1 has consumed from ring_in
+  // CTA0 only: ring feeding the T warp
+  float ring_t[V2_RING][32]; volatile u32 ring_t_seq_a[V2_RING]; volatile u32 ring_t_seq_b[V2_RING];
+  volatile u32 t_consumed;                   // both CTAs: bits the T warp has finished
+  // T warp scratch
+  float in1[L1_IN + 3], in2[L2_IN + 3];
+  alignas(16) float l1row[N_L1][ROW_PITCH_L1]; alignas(16) float l2row[ROW_PITCH_L2];
+  float l1extra[N_L1 + 4]; float mixp1[N_L1 + 4];
+  u32 slot1[N_L1 + 4];
+  float lut12[4100];                          // stretch LUT of the 12-bit replayed codes (+0.5 at 4096)
+};
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void spin_until_ge(volatile u32* p, u32 v) {
+  while (*p < v) { }
+}
+
+enum { BAR_READY = 1, BAR_COEFF = 2, BAR_MOVERS = 3 };
+#define V2_PROF(cond, slot) do { if (cond) { const long long now_ = clock64(); a.prof[slot] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
+
+__device__ __forceinline__ bool selector_is_bit_level(int sel) {
+  return sel == S_AUX || sel == S_LONGBIT || (sel >= S_BC0 && sel <= S_BC_RB1);
+}
+
+// Explicitly double-buffered serial chain (16 elements per block).
+__device__ __forceinline__ float chain_l0_v2(const float* __restrict__ x, const float* __restrict__ row) {
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* w4 = reinterpret_cast<const float4*>(row);
+  float p = 0.0f;
+  float4 xa[4], wa[4], xb[4], wb[4];
+#define CH_LOAD(X, W, blk) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { X[q] = x4[(blk) * 4 + q]; W[q] = w4[(blk) * 4 + q]; } }
+#define CH_EAT(X, W) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
+    p = XM_FADD(p, XM_FMUL(X[q].x, W[q].x)); p = XM_FADD(p, XM_FMUL(X[q].y, W[q].y)); \
+    p = XM_FADD(p, XM_FMUL(X[q].z, W[q].z)); p = XM_FADD(p, XM_FMUL(X[q].w, W[q].w)); } }
+  CH_LOAD(xa, wa, 0);
+#pragma unroll 1
+  for (int b = 0; b < 128; b += 2) {           // blocks 0..128 (129 blocks = 516 float4)
+    CH_LOAD(xb, wb, b + 1);
+    CH_EAT(xa, wa);
+    CH_LOAD(xa, wa, b + 2);
+    CH_EAT(xb, wb);
+  }
+  CH_EAT(xa, wa);                               // block 128
+#pragma unroll
+  for (int k = 516; k < 519; ++k) {
+    const float4 a = x4[k], b = w4[k];
+    p = XM_FADD(p, XM_FMUL(a.x, b.x)); p = XM_FADD(p, XM_FMUL(a.y, b.y));
+    p = XM_FADD(p, XM_FMUL(a.z, b.z)); p = XM_FADD(p, XM_FMUL(a.w, b.w));
+  }
+  p = XM_FADD(p, XM_FMUL(x[2076], row[2076]));
+  p = XM_FADD(p, XM_FMUL(x[2077], row[2077]));
+#undef CH_LOAD
+#undef CH_EAT
+  return p;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// movers: execute the row jobs (evictions first, then loads). Loads go global -> shared with
+// cp.async (LDGSTS, L1-bypassing), all in flight at once: one memory round trip per batch.
+__device__ __forceinline__ void run_row_jobs(MixShared2& sh, StreamState* st, int m0, int mtid) {
+  const int nj = sh.n_jobs;
+  const int per = ROW_PITCH_L0 / 4;            // 526 float4 per row
+  for (int idx = mtid; idx < nj * per; idx += V2_M_THREADS) {
+    const int j = idx / per, k = idx - j * per;
+    const RowJob jb = sh.jobs[j];
+    if (jb.do_evict) {
+      float4* g = reinterpret_cast<float4*>(st->mixer[m0 + jb.mixer].rows + (size_t)jb.evict_slot * ROW_PITCH_L0);
+      __stcg(&g[k], reinterpret_cast<const float4*>(sh.rows[jb.buf])[k]);
+    }
+  }
+  named_sync(BAR_MOVERS, V2_M_THREADS);
+  for (int idx = mtid; idx < nj * per; idx += V2_M_THREADS) {
+    const int j = idx / per, k = idx - j * per;
+    const RowJob jb = sh.jobs[j];
+    if (jb.do_load) {
+      const float4* g = reinterpret_cast<const float4*>(st->mixer[m0 + jb.mixer].rows + (size_t)jb.load_slot * ROW_PITCH_L0);
+      cp_async16(&reinterpret_cast<float4*>(sh.rows[jb.buf])[k], &g[k]);
+    }
+  }
+  if (mtid < nj) {
+    const RowJob jb = sh.jobs[mtid];
+    MixerState& m = st->mixer[m0 + jb.mixer];
+    if (jb.do_evict) m.row_steps[jb.evict_slot] = sh.steps[jb.buf];
+    if (jb.do_load) { sh.steps[jb.buf] = m.row_steps[jb.load_slot]; sh.tag[jb.buf] = jb.load_slot; sh.dirty[jb.buf] = 0; }
+  }
+  cp_async_wait_all();
+  named_sync(BAR_MOVERS, V2_M_THREADS);
+}
+
+// Stage the 2078 layer-0 inputs with all global loads issued before any use (2 round trips).
+__device__ __forceinline__ void stage_inputs_v2(float* x, const float* lut, const u16* ext, const float* small_x,
+                                                float lstm_x, int mtid) {
+  enum { PER = (N_INPUTS + V2_M_THREADS - 1) / V2_M_THREADS };   // 6
+  u32 code[PER]; float direct[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int k = mtid + q * V2_M_THREADS;
+    code[q] = 0x10000u; direct[q] = 0.0f;
+    if (k < N_INPUTS) {
+      if (k < 3) direct[q] = small_x[k];
+      else if (k < 3 + N_EXT) code[q] = ext ? (u32)__ldcs(&ext[k - 3]) : 0xFFFFu;
+      else if (k < 2076) direct[q] = small_x[k - N_EXT];
+      else if (k == 2076) direct[q] = small_x[N_SMALL];
+      else direct[q] = lstm_x;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int k = mtid + q * V2_M_THREADS;
+    if (k < N_INPUTS) x[k] = code[q] == 0x10000u ? direct[q] : lut[code[q] == 0xFFFFu ? 4096 : code[q]];
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MIX_THREADS, 1)
+mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const ChunkArgs a = args_all[blockIdx.x / 2];
+  StreamState* st = a.st;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MixShared2& sh = *reinterpret_cast<MixShared2*>(smem_raw);
+  MixShared2* sh0 = cluster.map_shared_rank(&sh, 0);
+  MixShared2* sh1 = cluster.map_shared_rank(&sh, 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = rank * MIX_PER_CTA;
+  const u64 n_bits = (u64)a.n_bytes * 8;
+
+  // ---------------- prologue: bookkeeping, buffers ----------------
+  if (tid == 0) {
+    int next = MIX_PER_CTA;
+    for (int i = 0; i < MIX_PER_CTA; ++i) {
+      sh.buf_cur[i] = i;
+      sh.buf_alt[i] = -1;
+      if (selector_is_bit_level(st->mixer[m0 + i].sel) && next < V2_NBUF) sh.buf_alt[i] = next++;
+      sh.max_steps[i] = st->mixer[m0 + i].max_steps;
+      sh.swap_needed[i] = 0; sh.late[i] = 0;
+    }
+    for (int b = 0; b < V2_NBUF; ++b) { sh.tag[b] = 0xffffffffu; sh.dirty[b] = 0; sh.steps[b] = 0; }
+    for (int r = 0; r < V2_RING; ++r) { sh.ring_in_seq[r] = 0; sh.ring_t_seq_a[r] = 0; sh.ring_t_seq_b[r] = 0; }
+    sh.peer_progress = 0; sh.t_consumed = 0; sh.n_jobs = 0;
+  }
+  for (int k = tid; k < 4097; k += MIX_THREADS) sh.lut12[k] = T.lut12[k];
+  __syncthreads();
+  cluster.sync();                               // both CTAs initialised before any DSMEM traffic
+
+  if (warp == V2_C_WARP) {
+    // =============================== C warp ===============================
+    const int i = lane;                         // local mixer
+    const float lr = lane < MIX_PER_CTA ? st->mixer[m0 + lane].lr : 0.0f;
+    const bool pc_on = a.prof != nullptr && lane == 0; const int pb = rank == 0 ? 8 : 14;
+    long long tprev = clock64();
+    for (u64 t = 0; t < n_bits; ++t) {
+      const int par = (int)(t & 1), r = (int)(t & (V2_RING - 1));
+      const int bit = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
+      const float decay = a.decay[t];
+      named_sync(BAR_READY, V2_CM_THREADS);
+      V2_PROF(pc_on, pb + 0);
+      const float* x = sh.x[par];
+      const float* row = sh.rows[lane < MIX_PER_CTA ? sh.buf_cur[lane] : 0];
+      float main = 0.0f;
+      if (lane < MIX_PER_CTA) main = chain_l0_v2(x, row);
+      __syncwarp();
+      V2_PROF(pc_on, pb + 1);
+      // ---- forward substitution through the extra inputs ----
+      float e = 0.0f, pfin = 0.0f;
+      int kbase = 0;
+      if (rank == 1) {
+        if (lane == 0) spin_until_ge(&sh.ring_in_seq[r], (u32)(t + 1));
+        __syncwarp();
+        fence_cluster();
+        if (lane < MIX_PER_CTA) {
+#pragma unroll
+          for (int k = 0; k < MIX_PER_CTA; ++k) e = XM_FADD(e, XM_FMUL(sh.ring_in[r][k], row[N_INPUTS + k]));
+        }
+        if (lane < MIX_PER_CTA) sh.extras[par][lane] = sh.ring_in[r][lane];
+        __syncwarp();
+        if (lane == 0) { fence_cluster(); sh0->peer_progress = (u32)(t + 1); }
+        kbase = MIX_PER_CTA;
+      }
+      V2_PROF(pc_on, pb + 2);
+      float cmine = 0.0f;
+      for (int k = 0; k < MIX_PER_CTA; ++k) {
+        if (lane == k) pfin = XM_FADD(main, e);
+        const float pk = __shfl_sync(0xffffffffu, pfin, k);
+        const float ck = clamp_stretched(T, pk);
+        if (lane == k) cmine = ck;
+        if (lane > k && lane < MIX_PER_CTA) e = XM_FADD(e, XM_FMUL(ck, row[N_INPUTS + kbase + k]));
+      }
+      V2_PROF(pc_on, pb + 3);
+      // ---- SGD coefficient (mixer.cpp:58-66) with the row's step counters held in shared memory ----
+      if (lane < MIX_PER_CTA) {
+        const int buf = sh.buf_cur[lane];
+        const u64 rs = sh.steps[buf];
+        const u64 ms = sh.max_steps[lane];
+        float d = decay;
+        d = (float)((double)d * (1.5 - ((1.0 * (double)rs) / (double)ms)));
+        const float u = XM_FMUL(XM_FMUL(d, lr), XM_FSUB(xm_logistic(pfin), (float)bit));
+        const u64 ns = rs + 1;
+        sh.steps[buf] = ns;
+        if (ns > ms) sh.max_steps[lane] = ns;
+        sh.upd[lane] = u;
+        sh.shrink[lane] = ((ns & 1023) == 0) ? 1u : 0u;
+        sh.extras[par][m0 + lane] = cmine;
+      }
+      __syncwarp();
+      V2_PROF(pc_on, pb + 4);
+      // ---- publish ----
+      if (rank == 0) {
+        // to CTA 1 (ring of 4; wait if it is 4 bits behind)
+        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.peer_progress, (u32)(t + 1 - V2_RING)); }
+        __syncwarp();
+        if (lane < MIX_PER_CTA) sh1->ring_in[r][lane] = cmine;
+        // to the T warp
+        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING)); }
+        __syncwarp();
+        if (lane < MIX_PER_CTA) sh.ring_t[r][lane] = cmine;
+        else if (lane < MIX_PER_CTA + 3) {
+          const int idx = lane == MIX_PER_CTA ? 433 : (lane == MIX_PER_CTA + 1 ? 2024 : 2077);
+          sh.ring_t[r][N_L0 + (lane - MIX_PER_CTA)] = clamp_stretched(T, x[idx]);
+        }
+        __syncwarp();
+        fence_cluster();
+        if (lane == 0) { sh1->ring_in_seq[r] = (u32)(t + 1); sh.ring_t_seq_a[r] = (u32)(t + 1); }
+      } else {
+        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING)); }
+        __syncwarp();
+        if (lane < MIX_PER_CTA) sh0->ring_t[r][MIX_PER_CTA + lane] = cmine;
+        __syncwarp();
+        fence_cluster();
+        if (lane == 0) sh0->ring_t_seq_b[r] = (u32)(t + 1);
+      }
+      V2_PROF(pc_on, pb + 5);
+      named_arrive(BAR_COEFF, V2_CM_THREADS);
+    }
+  } else if (warp < V2_T_WARP && (warp & 3) != 3) {
+    // =============================== M warps ===============================
+    const int mtid = (warp - (warp >> 2)) * 32 + lane;
+    const bool pm_on = a.prof != nullptr && mtid == 0 && rank == 0;
+    long long tprev = clock64();
+    for (u64 t = 0; t <= n_bits; ++t) {
+      // ---- prep bit t: inputs, selectors, rows ----
+      if (t < n_bits) {
+        const int par = (int)(t & 1);
+        // selectors other than auxiliary_context_ do not depend on the staged inputs: resolve them first
+        if (mtid < SEL_PITCH) sh.sel[par][mtid] = mtid < N_MIXERS ? a.sel[t * SEL_PITCH + mtid] : 0;
+        if (mtid >= 64 && mtid < 64 + MIX_PER_CTA && !(rank == 0 && mtid - 64 == 12))
+          sh.want[mtid - 64] = resolve_slot(st->mixer[m0 + mtid - 64], a.sel[t * SEL_PITCH + m0 + mtid - 64]);
+        stage_inputs_v2(sh.x[par], sh.lut12, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], mtid);
+        named_sync(BAR_MOVERS, V2_M_THREADS);
+        V2_PROF(pm_on, 20);
+        if (rank == 0 && mtid == 0) {
+          const u32 ax = aux_context(sh.x[par]);
+          sh.sel[par][12] = ax;
+          sh.want[12] = resolve_slot(st->mixer[12], ax);
+        }
+        if (mtid == 0) {
+          int nj = 0;
+          for (int i = 0; i < MIX_PER_CTA; ++i) {
+            const u32 s = sh.want[i];
+            const int cur = sh.buf_cur[i], alt = sh.buf_alt[i];
+            sh.swap_needed[i] = 0; sh.late[i] = 0;
+            if (sh.tag[cur] == s) continue;
+            if (alt >= 0) {
+              sh.swap_needed[i] = 1;
+              if (sh.tag[alt] == s) continue;
+              RowJob jb; jb.buf = alt; jb.mixer = i; jb.load_slot = s; jb.evict_slot = sh.tag[alt];
+              jb.do_evict = (sh.tag[alt] != 0xffffffffu && sh.dirty[alt]) ? 1 : 0; jb.do_load = 1;
+              sh.jobs[nj++] = jb;
+            } else {
+              sh.late[i] = 1;                   // single buffer: switch after the pending update
+            }
+          }
+          sh.n_jobs = nj;
+        }
+        named_sync(BAR_MOVERS, V2_M_THREADS);
+        V2_PROF(pm_on, 21);
+        run_row_jobs(sh, st, m0, mtid);         // prefetch into the spare buffers (overlaps the chains of bit t-1)
+      }
+      // ---- finish bit t-1: wait for its coefficients, apply the update ----
+      if (t > 0) {
+        const int parp = (int)((t - 1) & 1);
+        V2_PROF(pm_on, 22);
+        named_sync(BAR_COEFF, V2_CM_THREADS);
+        V2_PROF(pm_on, 23);
+        const float* xp = sh.x[parp];
+        const float* ex = sh.extras[parp];
+        for (int i = 0; i < MIX_PER_CTA; ++i) {
+          const float u = sh.upd[i];
+          const bool shr = sh.shrink[i] != 0;
+          float* row = sh.rows[sh.buf_cur[i]];
+          const int n = N_INPUTS + m0 + i;
+          for (int k = mtid; k < n; k += V2_M_THREADS) {
+            const float xin = k < N_INPUTS ? xp[k] : ex[k - N_INPUTS];
+            float w = XM_FSUB(row[k], XM_FMUL(u, xin));
+            if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+            row[k] = w;
+          }
+        }
+        if (mtid < MIX_PER_CTA) sh.dirty[sh.buf_cur[mtid]] = 1;
+        named_sync(BAR_MOVERS, V2_M_THREADS);
+        V2_PROF(pm_on, 24);
+      }
+      if (t < n_bits) {
+        // ---- make the rows of bit t current: swap prefetched buffers, late-switch single-buffer rows ----
+        if (mtid == 0) {
+          int nj = 0;
+          for (int i = 0; i < MIX_PER_CTA; ++i) {
+            if (sh.swap_needed[i]) { const int c = sh.buf_cur[i]; sh.buf_cur[i] = sh.buf_alt[i]; sh.buf_alt[i] = c; }
+            else if (sh.late[i]) {
+              const int cur = sh.buf_cur[i];
+              RowJob jb; jb.buf = cur; jb.mixer = i; jb.load_slot = sh.want[i]; jb.evict_slot = sh.tag[cur];
+              jb.do_evict = (sh.tag[cur] != 0xffffffffu && sh.dirty[cur]) ? 1 : 0; jb.do_load = 1;
+              sh.jobs[nj++] = jb;
+            }
+          }
+          sh.n_jobs = nj;
+        }
+        named_sync(BAR_MOVERS, V2_M_THREADS);
+        if (sh.n_jobs) run_row_jobs(sh, st, m0, mtid);
+        V2_PROF(pm_on, 25);
+        named_arrive(BAR_READY, V2_CM_THREADS);
+      }
+    }
+    // ---- epilogue: write every dirty resident row back ----
+    if (mtid == 0) {
+      int nj = 0;
+      for (int i = 0; i < MIX_PER_CTA; ++i) {
+        for (int w = 0; w < 2; ++w) {
+          const int b = w == 0 ? sh.buf_cur[i] : sh.buf_alt[i];
+          if (b < 0 || sh.tag[b] == 0xffffffffu || !sh.dirty[b]) continue;
+          RowJob jb; jb.buf = b; jb.mixer = i; jb.load_slot = 0; jb.evict_slot = sh.tag[b]; jb.do_evict = 1; jb.do_load = 0;
+          sh.jobs[nj++] = jb;
+        }
+        st->mixer[m0 + i].max_steps = sh.max_steps[i];
+      }
+      sh.n_jobs = nj;
+    }
+    named_sync(BAR_MOVERS, V2_M_THREADS);
+    run_row_jobs(sh, st, m0, mtid);
+  } else if (rank == 0 && warp == V2_T_WARP) {
+    // =============================== T warp (CTA 0, warp 14) ===============================
+    // Layers 1/2 + SSE, one bit behind the layer-0 recurrence. All HBM-latency-bound lookups
+    // (row tables, step counters, the 13 candidate SSE buckets) are issued BEFORE waiting for
+    // the layer-0 outputs, so their latency overlaps the chains.
+    SseState& sse = st->sse;
+    u32 sj = sse.j, spc = sse.pc, sffl = sse.ffl;                 // M_T::M_j / M_pc / M_ffl, warp-uniform
+    const u16* __restrict__ tst = sse.st; const u16* __restrict__ tsq = sse.sq;
+    MixerState& mym = st->mixer[N_L0 + (lane < N_L1 + 1 ? lane : 0)];
+    float* const myrows = mym.rows; u64* const mysteps = mym.row_steps; u32* const mytable = mym.slot_table;
+    const float mylr = mym.lr;
+    u64 my_max = mym.max_steps; u32 my_assigned = mym.n_assigned; const u32 my_nrows = mym.n_rows;
+    const bool pt_on = a.prof != nullptr && lane == 0;
+    long long tprev = clock64();
+    u32 myslot = 0xffffffffu; u64 my_rs = 0;
+    for (u64 t = 0; t < n_bits; ++t) {
+      const int r = (int)(t & (V2_RING - 1));
+      const int bit = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
+      // ---- candidate SSE buckets for every possible quantisation of p (sse.cpp:250-270) ----
+      uint4 cand = make_uint4(0, 0, 0, 0); size_t cand_idx = 0;
+      if (lane < 3) {
+        cand_idx = (((((size_t)lane << 7) + (sffl & 127)) << 8) + (spc & 255)) * 256 + sj;                 // sm6x
+        cand = *reinterpret_cast<const uint4*>(sse.s6 + cand_idx * 8);
+      } else if (lane < 6) {
+        cand_idx = (((((size_t)(lane - 3) << 5) + (sffl & 31)) << 8) + (spc & 255)) * 255 + (sj < 2 ? 0 : sj - 1);   // sm7x
+        cand = *reinterpret_cast<const uint4*>(sse.s7 + cand_idx * 8);
+      } else if (lane < 9) {
+        cand_idx = (((((size_t)(lane - 6) << 1) + (sffl & 1)) << 8) + (spc & 255)) * 256 + sj;             // mix2
+        cand.x = (u32)sse.x2[cand_idx];
+      } else if (lane < 13) {
+        cand_idx = (((((size_t)(lane - 9) << 8) + (sffl & 255)) << 3) + ((spc >> 5) & 7)) * 79 + sse_mask1((int)sj);   // mix1
+        cand.x = (u32)sse.x1[cand_idx];
+      }
+      // ---- rows of layers 1/2: lane i keeps the selected row of mixer 26+i resident in shared memory ----
+      if (lane < N_L1 + 1) {
+        const u32 ctx = a.sel[t * SEL_PITCH + N_L0 + lane];
+        u32 sl = mytable[ctx];
+        if (sl == 0) {
+          const u32 cap = my_nrows - 1;
+          if (my_assigned < cap && my_assigned < (u32)SLOT_LIMIT) { sl = ++my_assigned; mytable[ctx] = sl; }
+          else sl = my_nrows;
+        }
+        const u32 want = sl - 1;
+        if (want != myslot) {
+          float4* srow = reinterpret_cast<float4*>(lane < N_L1 ? sh.l1row[lane] : sh.l2row);
+          if (myslot != 0xffffffffu) {
+            float4* g = reinterpret_cast<float4*>(myrows + (size_t)myslot * ROW_PITCH_L1);
+#pragma unroll
+            for (int q = 0; q < ROW_PITCH_L1 / 4; ++q) g[q] = srow[q];
+            mysteps[myslot] = my_rs;
+          }
+          const float4* g = reinterpret_cast<const float4*>(myrows + (size_t)want * ROW_PITCH_L1);
+          float4 tmp[ROW_PITCH_L1 / 4];
+#pragma unroll
+          for (int q = 0; q < ROW_PITCH_L1 / 4; ++q) tmp[q] = g[q];
+          my_rs = mysteps[want];
+#pragma unroll
+          for (int q = 0; q < ROW_PITCH_L1 / 4; ++q) srow[q] = tmp[q];
+          myslot = want;
+        }
+      }
+      __syncwarp();
+      V2_PROF(pt_on, 26);
+      // ---- wait for the 26 clamped layer-0 outputs + 3 auxiliary inputs of bit t ----
+      if (lane == 0) { spin_until_ge(&sh.ring_t_seq_a[r], (u32)(t + 1)); spin_until_ge(&sh.ring_t_seq_b[r], (u32)(t + 1)); }
+      __syncwarp();
+      V2_PROF(pt_on, 27);
+      fence_cluster();
+      if (lane < N_L0) { const float c = sh.ring_t[r][lane]; sh.in1[lane] = c; sh.in2[lane] = c; }
+      if (lane < N_AUX) { const float c = sh.ring_t[r][N_L0 + lane]; sh.in1[N_L0 + lane] = c; sh.in2[N_L0 + N_L1 + lane] = c; }
+      __syncwarp();
+      if (lane == 0) { fence_cluster(); sh.t_consumed = (u32)(t + 1); sh1->t_consumed = (u32)(t + 1); }
+      // ---- layer 1 ----
+      float main = 0.0f;
+      if (lane < N_L1) {
+        const float* w = sh.l1row[lane];
+#pragma unroll
+        for (int k = 0; k < L1_IN; ++k) main = XM_FADD(main, XM_FMUL(sh.in1[k], w[k]));
+      }
+      float e = 0.0f, pfin = 0.0f;
+      for (int k = 0; k < N_L1; ++k) {
+        if (lane == k) pfin = XM_FADD(main, e);
+        const float pk = __shfl_sync(0xffffffffu, pfin, k);
+        const float ck = clamp_stretched(T, pk);
+        if (lane == k) { sh.l1extra[k] = ck; sh.in2[N_L0 + k] = ck; }
+        if (lane > k && lane < N_L1) e = XM_FADD(e, XM_FMUL(ck, sh.l1row[lane][L1_IN + k]));
+      }
+      __syncwarp();
+      // ---- layer 2 (lane 20 owns the mixer; computed by all lanes redundantly is not needed) ----
+      float s2 = 0.0f;
+      if (lane == N_L1) {
+#pragma unroll
+        for (int k = 0; k < L2_IN; ++k) s2 = XM_FADD(s2, XM_FMUL(sh.in2[k], sh.l2row[k]));
+        s2 = XM_FADD(s2, 0.0f);
+        pfin = s2;
+      }
+      s2 = __shfl_sync(0xffffffffu, s2, N_L1);
+      // ---- SSE (sse.cpp:243-289) on the prefetched buckets; all lanes run the scalar code uniformly ----
+      const float pin = xm_logistic(s2);
+      const int discrete = (int)XM_FADD(1.0f, XM_FMUL(XM_FSUB(1.0f, pin), 32766.0f));
+      const u32 prq = (u32)discrete >> 11;
+      const int q3 = (prq > 0) + (prq > 14), q4 = (prq > 0) + (prq > 7) + (prq > 14);
+      const uint4 b6 = make_uint4(__shfl_sync(0xffffffffu, cand.x, q3), __shfl_sync(0xffffffffu, cand.y, q3),
+                                  __shfl_sync(0xffffffffu, cand.z, q3), __shfl_sync(0xffffffffu, cand.w, q3));
+      const uint4 b7 = make_uint4(__shfl_sync(0xffffffffu, cand.x, 3 + q3), __shfl_sync(0xffffffffu, cand.y, 3 + q3),
+                                  __shfl_sync(0xffffffffu, cand.z, 3 + q3), __shfl_sync(0xffffffffu, cand.w, 3 + q3));
+      int wx2 = (int)__shfl_sync(0xffffffffu, cand.x, 6 + q3);
+      int wx1 = (int)__shfl_sync(0xffffffffu, cand.x, 9 + q4);
+      const size_t i6 = __shfl_sync(0xffffffffu, (unsigned long long)cand_idx, q3);
+      const size_t i7 = __shfl_sync(0xffffffffu, (unsigned long long)cand_idx, 3 + q3);
+      const size_t ix2 = __shfl_sync(0xffffffffu, (unsigned long long)cand_idx, 6 + q3);
+      const size_t ix1 = __shfl_sync(0xffffffffu, (unsigned long long)cand_idx, 9 + q4);
+      u16 k6[8] = {(u16)b6.x, (u16)(b6.x >> 16), (u16)b6.y, (u16)(b6.y >> 16), (u16)b6.z, (u16)(b6.z >> 16), (u16)b6.w, (u16)(b6.w >> 16)};
+      u16 k7[8] = {(u16)b7.x, (u16)(b7.x >> 16), (u16)b7.y, (u16)(b7.y >> 16), (u16)b7.z, (u16)(b7.z >> 16), (u16)b7.w, (u16)(b7.w >> 16)};
+      if (lane == 0) {
+        const int stp = __ldg(&tst[discrete]);
+        int sw6, qq6, P6, sw7, qq7, P7;
+        const int p1 = sse_pred(k6, __ldg(&tsq[sse_extrap(stp, 10240)]), &sw6, &qq6, &P6);
+        const int s0 = sse_extrap(stp, 7935);
+        const int s1 = sse_extrap(__ldg(&tst[p1]), 9592);
+        int sm = sse_mixup(wx1, s0, s1);
+        sm = sse_extrap(sm, 8092);
+        const int mix1_p = __ldg(&tsq[sm]);
+        const int p2 = sse_pred(k7, __ldg(&tsq[sse_extrap(stp, 8200)]), &sw7, &qq7, &P7);
+        const int s4 = sse_extrap(__ldg(&tst[p2]), 7677);
+        int s5 = sse_mixup(wx2, sm, s4);
+        s5 = sse_extrap(s5, 8202);
+        const int mix2_p = __ldg(&tsq[s5]);
+        const float p = (float)(1.0 - ((double)(mix2_p - 1) / 32766.0));
+        const float ov = a.lstm_x[2 * t + 1];
+        a.p_out[t] = ov >= 0.0f ? ov : p;
+        // M_Update (sse.cpp:291-305)
+        sse_bucket_update(k6, bit, 106, sw6, qq6, P6);
+        sse_mix_update(&wx1, bit, s0, s1, 6202, mix1_p);
+        sse_bucket_update(k7, bit, 127, sw7, qq7, P7);
+        sse_mix_update(&wx2, bit, sm, s4, 8320, mix2_p);
+        u16* g6 = sse.s6 + i6 * 8; g6[qq6] = k6[qq6]; g6[qq6 + 1] = k6[qq6 + 1];
+        u16* g7 = sse.s7 + i7 * 8; g7[qq7] = k7[qq7]; g7[qq7 + 1] = k7[qq7 + 1];
+        sse.x1[ix1] = wx1; sse.x2[ix2] = wx2;
+      }
+      sj += sj + bit;
+      if (sj >= 256) { sffl = (u8)(sffl * 2 + (spc >= 0x40)); spc = (u8)sj; sj = 1; }
+      // ---- SGD of layers 1/2 (mixer.cpp:56-72) on the lane-owned resident rows ----
+      const float decay = a.decay[t];
+      if (lane < N_L1 + 1) {
+        float d = decay;
+        d = (float)((double)d * (1.5 - ((1.0 * (double)my_rs) / (double)my_max)));
+        const float u = XM_FMUL(XM_FMUL(d, mylr), XM_FSUB(xm_logistic(pfin), (float)bit));
+        my_rs += 1;
+        if (my_rs > my_max) my_max = my_rs;
+        const bool shr = (my_rs & 1023) == 0;
+        float* row = lane < N_L1 ? sh.l1row[lane] : sh.l2row;
+        const int n = lane < N_L1 ? L1_IN + lane : L2_IN;
+        for (int c = 0; c < n; ++c) {
+          const float xin = lane < N_L1 ? (c < L1_IN ? sh.in1[c] : sh.l1extra[c - L1_IN]) : sh.in2[c];
+          float w = XM_FSUB(row[c], XM_FMUL(u, xin));
+          if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+          row[c] = w;
+        }
+      }
+      __syncwarp();
+      __threadfence_block();
+      V2_PROF(pt_on, 28);
+    }
+    if (lane < N_L1 + 1) {
+      if (myslot != 0xffffffffu) {
+        const float* srow = lane < N_L1 ? sh.l1row[lane] : sh.l2row;
+        float* g = myrows + (size_t)myslot * ROW_PITCH_L1;
+        for (int q = 0; q < ROW_PITCH_L1; ++q) g[q] = srow[q];
+        mysteps[myslot] = my_rs;
+      }
+      mym.max_steps = my_max; mym.n_assigned = my_assigned;
+    }
+    if (lane == 0) { sse.j = sj; sse.pc = spc; sse.ffl = sffl; st->bits_done += n_bits; }
+  }
+  __syncthreads();
+  cluster.sync();                               // nobody exits while a peer may still address its shared memory
+}
+
+}  // namespace cmixb200
