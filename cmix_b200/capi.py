@@ -58,6 +58,10 @@ def load_library():
     lib.cmixb200_last_error.restype = c.c_char_p
     lib.cmixb200_kernel_launches.argtypes = [vp]
     lib.cmixb200_kernel_launches.restype = c.c_ulonglong
+    lib.cmixb200_time_mix_kernel.argtypes = [vp, c.c_int]
+    lib.cmixb200_time_mix_kernel.restype = None
+    lib.cmixb200_mix_kernel_ms.argtypes = [vp, c.POINTER(c.c_ulonglong)]
+    lib.cmixb200_mix_kernel_ms.restype = c.c_double
     lib.cmixb200_mix_stream.argtypes = [vp]
     lib.cmixb200_mix_stream.restype = vp
     lib.cmixb200_debug_fetch.argtypes = [vp, c.c_int, vp, c.c_size_t]
@@ -150,6 +154,14 @@ class Predictor:
     @property
     def kernel_launches(self):
         return int(self._lib.cmixb200_kernel_launches(self._h))
+
+    def time_mix_kernel(self, enable=True):
+        self._lib.cmixb200_time_mix_kernel(self._h, 1 if enable else 0)
+
+    def mix_kernel_ms(self):
+        n = ctypes.c_ulonglong(0)
+        ms = self._lib.cmixb200_mix_kernel_ms(self._h, ctypes.byref(n))
+        return float(ms), int(n.value)
 
     @property
     def mix_stream(self):

@@ -268,6 +268,8 @@ struct cmixb200_predictor {
   float* d_ppmd_byte = nullptr; bool ppmd_byte_valid = false;
   unsigned long long launches = 0;
   unsigned long long* d_prof = nullptr;
+  bool time_mix = false; double mix_ms = 0.0; unsigned long long mix_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_ev;
   u8 vocab[256];
   int V = 0;
 
@@ -465,6 +467,15 @@ void FillDecay(std::vector<float>& out, u64 steps0, size_t n_bits) {
   }
 }
 
+void HarvestMixTimes(cmixb200_predictor* P) {
+  for (auto& ev : P->pending_ev) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) { P->mix_ms += ms; P->mix_launches++; }
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  P->pending_ev.clear();
+}
+
 // Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain) {
   const Tables T = g_tables.T;
@@ -482,9 +493,12 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
     CK(cudaStreamWaitEvent(lead->s_mix, e1, 0));
     CK(cudaStreamWaitEvent(lead->s_mix, e2, 0));
     static const bool use_v1 = getenv("CMIXB200_MIX_V1") != nullptr;   // barrier-per-phase reference version of the kernel
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (lead->time_mix) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, lead->s_mix)); }
     if (use_v1) mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
     else mix_kernel_v2<<<2 * n_streams, MIX_THREADS, sizeof(MixShared2), lead->s_mix>>>(d_args, T);
     lead->launches++;
+    if (lead->time_mix) { CK(cudaEventRecord(t1, lead->s_mix)); lead->pending_ev.push_back({t0, t1}); }
     CK(cudaEventDestroy(e1));
     CK(cudaEventDestroy(e2));
   }
@@ -492,46 +506,62 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
   return CMIXB200_OK;
 }
 
-int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u16* d_ext, const float* d_ppmd,
-               float* d_p_out, bool pretrain) {
-  if (n_bytes == 0) return CMIXB200_OK;
-  if (P->bit_context != 1) { g_last_error = "bulk coding must start on a byte boundary"; return CMIXB200_ERR_ARG; }
-  CK(cudaSetDevice(P->device));
-  TRY(EnsureScratch(P, n_bytes));
-  if (!pretrain) {
-    std::vector<float> decay;
-    FillDecay(decay, P->bits_done, n_bytes * 8);
-    CK(cudaMemcpyAsync(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice, P->s_mix));
-    CK(cudaStreamSynchronize(P->s_mix));
-  }
-  // Software pipeline over sub-chunks: the two producer kernels (small models, LSTM) of sub-chunk
-  // k+1 run on their own streams while the mixer consumes sub-chunk k.
+// Advance n_streams predictors (same device) by n_bytes each. Software pipeline over sub-chunks:
+// the two producer kernels (small models, LSTM) of sub-chunk k+1 run on their own CUDA streams
+// while the mixer consumes sub-chunk k. All pointers are device pointers.
+int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_bytes, size_t n_bytes,
+                 const u16* const* d_ext, const float* const* d_ppmd, float* const* d_p_out, bool pretrain) {
+  if (n_bytes == 0 || n_streams <= 0) return CMIXB200_OK;
+  cmixb200_predictor* lead = preds[0];
+  CK(cudaSetDevice(lead->device));
   static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 512;
   const size_t n_sub = pretrain ? 1 : (n_bytes + kSub - 1) / kSub;
-  std::vector<ChunkArgs> args(n_sub);
-  for (size_t k = 0; k < n_sub; ++k) {
-    const size_t off = pretrain ? 0 : k * kSub;
-    const size_t n = pretrain ? n_bytes : (n_bytes - off < kSub ? n_bytes - off : kSub);
-    ChunkArgs& a = args[k];
-    memset(&a, 0, sizeof a);
-    a.st = P->d_st; a.bytes = d_bytes + off;
-    a.ext = d_ext ? d_ext + off * 8 * N_EXT : nullptr;
-    a.ppmd = d_ppmd ? d_ppmd + off * 256 : nullptr;
-    a.decay = P->d_decay + off * 8;
-    a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
-    a.lstm_x = P->d_lstm_x + off * 8 * 2; a.p_out = d_p_out ? d_p_out + off * 8 : nullptr;
-    a.n_bytes = (u32)n; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
+  std::vector<ChunkArgs> args(n_sub * n_streams);
+  std::vector<float> decay;
+  for (int s = 0; s < n_streams; ++s) {
+    cmixb200_predictor* P = preds[s];
+    if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
+    TRY(EnsureScratch(P, n_bytes));
+    if (!pretrain) {
+      FillDecay(decay, P->bits_done, n_bytes * 8);
+      CK(cudaMemcpy(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
+    }
+    for (size_t k = 0; k < n_sub; ++k) {
+      const size_t off = pretrain ? 0 : k * kSub;
+      const size_t n = pretrain ? n_bytes : (n_bytes - off < kSub ? n_bytes - off : kSub);
+      ChunkArgs& a = args[k * n_streams + s];
+      memset(&a, 0, sizeof a);
+      a.st = P->d_st; a.bytes = d_bytes[s] + off;
+      a.ext = (d_ext && d_ext[s]) ? d_ext[s] + off * 8 * N_EXT : nullptr;
+      a.ppmd = (d_ppmd && d_ppmd[s]) ? d_ppmd[s] + off * 256 : nullptr;
+      a.decay = P->d_decay + off * 8;
+      a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
+      a.lstm_x = P->d_lstm_x + off * 8 * 2;
+      a.p_out = (d_p_out && d_p_out[s]) ? d_p_out[s] + off * 8 : nullptr;
+      a.n_bytes = (u32)n; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
+    }
   }
-  if (P->n_args < n_sub) {
-    if (P->d_args) cudaFree(P->d_args);
-    CK(cudaMalloc(&P->d_args, sizeof(ChunkArgs) * n_sub));
-    P->n_args = n_sub;
+  if (lead->n_args < args.size()) {
+    if (lead->d_args) cudaFree(lead->d_args);
+    lead->d_args = nullptr;
+    CK(cudaMalloc(&lead->d_args, sizeof(ChunkArgs) * args.size()));
+    lead->n_args = args.size();
   }
-  CK(cudaMemcpy(P->d_args, args.data(), sizeof(ChunkArgs) * n_sub, cudaMemcpyHostToDevice));
-  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(P, P->d_args + k, 1, pretrain));
-  CK(cudaStreamSynchronize(P->s_small));
-  if (!pretrain) { CK(cudaStreamSynchronize(P->s_lstm)); CK(cudaStreamSynchronize(P->s_mix)); P->bits_done += n_bytes * 8; }
+  CK(cudaMemcpy(lead->d_args, args.data(), sizeof(ChunkArgs) * args.size(), cudaMemcpyHostToDevice));
+  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(lead, lead->d_args + k * n_streams, n_streams, pretrain));
+  CK(cudaStreamSynchronize(lead->s_small));
+  if (!pretrain) {
+    CK(cudaStreamSynchronize(lead->s_lstm));
+    CK(cudaStreamSynchronize(lead->s_mix));
+    for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
+  }
+  HarvestMixTimes(lead);
   return CMIXB200_OK;
+}
+
+int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u16* d_ext, const float* d_ppmd,
+               float* d_p_out, bool pretrain) {
+  return RunPipelined(&P, 1, &d_bytes, n_bytes, &d_ext, &d_ppmd, &d_p_out, pretrain);
 }
 
 }  // namespace
@@ -679,39 +709,12 @@ int cmixb200_pretrain_bytes(cmixb200_predictor* P, const uint8_t* bytes, size_t 
 
 int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes, size_t n_bytes,
                                const uint16_t* const* d_ext, const float* const* d_ppmd, float* const* d_p_out) {
-  if (n_streams <= 0 || n_bytes == 0) return CMIXB200_OK;
-  cmixb200_predictor* lead = preds[0];
-  CK(cudaSetDevice(lead->device));
-  std::vector<ChunkArgs> args(n_streams);
-  std::vector<float> decay;
-  for (int s = 0; s < n_streams; ++s) {
-    cmixb200_predictor* P = preds[s];
-    if (P->device != lead->device || P->bit_context != 1) { g_last_error = "batch: streams must share a device and be byte aligned"; return CMIXB200_ERR_ARG; }
-    TRY(EnsureScratch(P, n_bytes));
-    FillDecay(decay, P->bits_done, n_bytes * 8);
-    CK(cudaMemcpy(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
-    ChunkArgs& a = args[s];
-    memset(&a, 0, sizeof a);
-    a.st = P->d_st; a.bytes = d_bytes[s]; a.ext = d_ext ? d_ext[s] : nullptr; a.ppmd = d_ppmd ? d_ppmd[s] : nullptr;
-    a.decay = P->d_decay; a.small_x = P->d_small_x; a.sel = P->d_sel; a.lstm_x = P->d_lstm_x; a.p_out = d_p_out[s];
-    a.n_bytes = (u32)n_bytes;
-  }
-  ChunkArgs* d_args = nullptr;
-  CK(cudaMalloc(&d_args, sizeof(ChunkArgs) * n_streams));
-  CK(cudaMemcpy(d_args, args.data(), sizeof(ChunkArgs) * n_streams, cudaMemcpyHostToDevice));
-  int r = LaunchChunk(lead, d_args, n_streams, false);
-  if (r == CMIXB200_OK) {
-    cudaError_t e = cudaStreamSynchronize(lead->s_small);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(lead->s_lstm);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(lead->s_mix);
-    if (e != cudaSuccess) { g_last_error = std::string("batch: ") + cudaGetErrorString(e); r = CMIXB200_ERR_CUDA; }
-  }
-  cudaFree(d_args);
-  if (r == CMIXB200_OK) for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
-  return r;
+  return RunPipelined(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, false);
 }
 
 unsigned long long cmixb200_kernel_launches(const cmixb200_predictor* P) { return P->launches; }
+void cmixb200_time_mix_kernel(cmixb200_predictor* P, int enable) { P->time_mix = enable != 0; if (enable) { P->mix_ms = 0; P->mix_launches = 0; } }
+double cmixb200_mix_kernel_ms(const cmixb200_predictor* P, unsigned long long* n_launches) { if (n_launches) *n_launches = P->mix_launches; return P->mix_ms; }
 void* cmixb200_mix_stream(cmixb200_predictor* P) { return (void*)P->s_mix; }
 
 int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t bytes) {

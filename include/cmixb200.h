@@ -69,6 +69,10 @@ int cmixb200_pretrain_bytes(cmixb200_predictor*, const uint8_t* bytes, size_t n_
 const char* cmixb200_last_error(void);
 /* kernels launched by this predictor so far (bench.py's gpu_launches). */
 unsigned long long cmixb200_kernel_launches(const cmixb200_predictor*);
+/* CUDA-event timing of the mixer kernel on the stream it is launched on (bench.py's roofline):
+ * enable, run bulk calls, then read the accumulated milliseconds and launch count. */
+void cmixb200_time_mix_kernel(cmixb200_predictor*, int enable);
+double cmixb200_mix_kernel_ms(const cmixb200_predictor*, unsigned long long* n_launches);
 /* the cudaStream_t the mixer kernel runs on (for CUDA-event timing in bench.py). */
 void* cmixb200_mix_stream(cmixb200_predictor*);
 
