@@ -242,7 +242,7 @@ int BuildSharedTables(int device) {
   CK(cudaFuncSetAttribute(mix_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared2)));
   CK(cudaFuncSetAttribute(mix_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
-  CK(cudaFuncSetAttribute(lstm_perceive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
+  CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   g_tables.ready = true;
   g_tables.device = device;
   return CMIXB200_OK;
@@ -420,11 +420,11 @@ int BuildStream(cmixb200_predictor* P) {
       auto rnd = [&]() { return static_cast<float>(rng.next()) / static_cast<float>(RAND_MAX); };
       for (int i = 0; i < C; ++i) {
         for (int j = 0; j < row; ++j) {
-          w[0][(size_t)j * C + i] = low + rnd() * range;
-          w[1][(size_t)j * C + i] = low + rnd() * range;
-          w[2][(size_t)j * C + i] = low + rnd() * range;
+          w[0][lstm_widx(row, j, i)] = low + rnd() * range;
+          w[1][lstm_widx(row, j, i)] = low + rnd() * range;
+          w[2][lstm_widx(row, j, i)] = low + rnd() * range;
         }
-        w[0][(size_t)(row - 1) * C + i] = 1;
+        w[0][lstm_widx(row, row - 1, i)] = 1;
       }
       for (int g = 0; g < 3; ++g) {
         GateState& G = Y.gate[g];
@@ -482,7 +482,7 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
   small_kernel<<<n_streams, 64, 0, lead->s_small>>>(d_args, T);
   lead->launches++;
   if (!pretrain) {
-    lstm_kernel<<<n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
+    lstm_kernel<<<LSTM_CTAS * n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
     lead->launches++;
     // the mixer consumes what the two producers write: order it after both
     cudaEvent_t e1, e2;
@@ -646,7 +646,8 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
   small_perceive_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, bit, ppmd, 0);
   mix_perceive_kernel<<<1, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
-  lstm_perceive_kernel<<<1, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, bit, byte_done ? 1 : 0, full, ppmd);
+  lstm_bit_kernel<<<1, 32, 0, P->s_mix>>>(P->d_st, bit);
+  if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
   P->launches += 3;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(P->s_mix));

@@ -7,258 +7,362 @@
 //
 // Parity contract: every floating-point result is bit-identical to the strict-FP
 // reference. That fixes the ORDER of every sum (the reference's scalar loops and
-// libstdc++'s valarray reductions), so parallelism comes only from the
-// independent chains: 600 gate rows per layer in the forward pass, 200 columns in
-// the transposed mat-vecs, and ~1M independent weight elements in the
-// weight-gradient accumulation, which is restructured from "100 rank-1 updates"
-// into one pass where each thread owns one weight and adds its 100 terms in the
-// reference's time order (99 -> 0) — same values, ~100x less memory traffic.
+// libstdc++'s valarray reductions: valarray::sum() front-to-back, _Expr::sum()
+// back-to-front), so parallelism comes only from independent chains: 600 gate
+// rows per layer in the forward pass, 200 columns in the transposed mat-vecs and
+// ~1M independent weight elements in the weight-gradient accumulation, which is
+// restructured from "100 rank-1 updates" into one pass where each thread owns one
+// weight and adds its 100 terms in the reference's time order (99 -> 0).
 // Tensor cores are deliberately not used: tcgen05 kinds round products to
-// TF32/BF16 and accumulate in an unspecified order, either of which breaks the
-// bit-exact contract.
+// TF32/BF16 and accumulate in an unspecified order; either breaks bit-exactness
+// (DESIGN.md §6).
+//
+// Layout: one thread-block CLUSTER of 8 CTAs per stream. CTA c owns cells
+// [25c, 25c+25) of every gate of both layers, and rows [32c, 32c+32) of the
+// softmax layer. Weights are stored cell-block-major ([cta][column][25 cells]) so
+// that a CTA's slice is one contiguous range that it stages into shared memory
+// with cp.async (all 512 threads, L1-bypassing) before its 75 serial chains run
+// out of shared memory. Vectors every CTA needs in full (gate pre-activations for
+// the RMS norm, hidden state, gate errors, softmax logits) are all-gathered with
+// distributed-shared-memory stores + one cluster barrier.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "exact_math.h"
 #include "small_models.cuh"
 #include "state.h"
 
 namespace cmixb200 {
+namespace cgl = cooperative_groups;
 
-enum { LSTM_THREADS = 1024 };
+enum { LSTM_THREADS = 512, LSTM_CTAS = 8, LCPC = 25 /* cells per CTA */, LSTM_POOL_FLOATS = 52224 /* 204 KB */ };
 #define LC LSTM_CELLS
 #define LH LSTM_HORIZON
 
+__host__ __device__ __forceinline__ size_t lstm_widx(int row, int col, int cell) {
+  return ((size_t)(cell / LCPC) * row + col) * LCPC + (cell % LCPC);
+}
+
 struct LstmShared {
-  float in[2 * 256 + 2 * LC + 8];     // current layer input vector
-  float norm[3][LC];
-  float e[3][LC];
-  float act[3][LC];
-  float tmp[3][LC];
-  float tmp2[3][LC];
-  float vec[LC];
-  float out[256];
+  float in[2 * 256 + 2 * LC + 8];   // current layer input vector
+  float gat[3][LC];                  // all-gathered per-gate vector (pre-activations / scaled errors)
+  float gat2[3][LC];                 // all-gathered final gate errors
+  float hid[LSTM_HID + 3];           // full hidden vector (all-gathered)
+  float act[3][LCPC];                // own cells: gate activations
+  float eown[3][LCPC];               // own cells: gate errors
+  float nown[3][LCPC];               // own cells: norm values of the step
+  float logits[256];                 // all-gathered softmax logits / exps
   float err[256];
-  float red[32];
-  float scal[8];
+  float scal[16];
   int sym[LH];
+  alignas(16) float pool[LSTM_POOL_FLOATS];
 };
 
 __device__ __forceinline__ float clipf(float v, float c) { return v < -c ? -c : (v > c ? c : v); }
 
-// LstmLayer::ForwardPass (lstm-layer.cpp:62-99) for one layer; all threads of the CTA.
-__device__ void lstm_layer_forward(LayerState& L, int V, int sym, float* hidden_out, LstmShared& sh, int tid) {
-  const int e = L.epoch;
-  const int in_size = L.in_size;
+__device__ __forceinline__ void lcp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void lcp_async4(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void lcp_async_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// all-gather: value of (gate g, own cell i) from every CTA into dst[g][25*rank + i] of every CTA
+__device__ __forceinline__ void gather75(cgl::cluster_group& cluster, float (*dst)[LC], int rank, int tid, float v) {
+  if (tid < 3 * LCPC) {
+    const int g = tid / LCPC, i = tid % LCPC;
+#pragma unroll
+    for (int c = 0; c < LSTM_CTAS; ++c) {
+      float (*rd)[LC] = cluster.map_shared_rank(dst, c);
+      rd[g][LCPC * rank + i] = v;
+    }
+  }
+}
+
+// LstmLayer::ForwardPass (lstm-layer.cpp:62-99) for one layer; the whole cluster.
+__device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, int l, int sym, LstmShared& sh, int rank, int tid) {
+  LayerState& L = S.layer[l];
+  const int V = S.V, e = L.epoch, in_size = L.in_size, row = in_size + V;
   const float* in_g = L.input + (size_t)e * in_size;
+  // ---- stage: input vector + this CTA's weight slice (dense columns, then the symbol column) ----
   for (int j = tid; j < in_size; j += LSTM_THREADS) sh.in[j] = in_g[j];
+  const int n4 = in_size * LCPC / 4;           // floats per gate slice, dense part (in_size*25 is a multiple of 4? see below)
+  for (int g = 0; g < 3; ++g) {
+    const float* src = L.gate[g].w + ((size_t)rank * row + V) * LCPC;     // [col >= V][25]
+    float* dst = sh.pool + (size_t)g * (in_size + 1) * LCPC;
+    const int nflt = in_size * LCPC;
+    // 16-byte copies where both sides are aligned; tail / unaligned with 4-byte copies
+    const bool al = ((((size_t)src) | ((size_t)dst)) & 15) == 0;
+    if (al) {
+      for (int k = tid; k < nflt / 4; k += LSTM_THREADS) lcp_async16(dst + 4 * k, src + 4 * k);
+      for (int k = (nflt / 4) * 4 + tid; k < nflt; k += LSTM_THREADS) lcp_async4(dst + k, src + k);
+    } else {
+      for (int k = tid; k < nflt; k += LSTM_THREADS) lcp_async4(dst + k, src + k);
+    }
+    const float* ssrc = L.gate[g].w + ((size_t)rank * row + sym) * LCPC;   // column `sym`
+    if (tid < LCPC) lcp_async4(dst + nflt + tid, ssrc + tid);
+  }
+  (void)n4;
+  lcp_async_wait();
   __syncthreads();
-  if (tid < 3 * LC) {
-    const int g = tid / LC, i = tid % LC;
-    const float* w = L.gate[g].w;
-    float f = w[(size_t)sym * LC + i];
-    const float* wc = w + (size_t)V * LC + i;
+  // ---- 75 serial chains out of shared memory ----
+  float f = 0.0f;
+  if (tid < 96 && (tid & 31) < LCPC) {
+    const int g = tid >> 5, i = tid & 31;
+    const float* w = sh.pool + (size_t)g * (in_size + 1) * LCPC + i;
+    f = w[(size_t)in_size * LCPC];
 #pragma unroll 8
-    for (int j = 0; j < in_size; ++j) f = XM_FADD(f, XM_FMUL(sh.in[j], wc[(size_t)j * LC]));
-    sh.norm[g][i] = f;
+    for (int j = 0; j < in_size; ++j) f = XM_FADD(f, XM_FMUL(sh.in[j], w[(size_t)j * LCPC]));
+#pragma unroll
+    for (int c = 0; c < LSTM_CTAS; ++c) {
+      float (*rd)[LC] = cluster.map_shared_rank(sh.gat, c);
+      rd[g][LCPC * rank + i] = f;
+    }
   }
-  __syncthreads();
-  if (tid < 96 && (tid & 31) == 0) {          // one lane per gate: _Expr::sum() adds back to front
+  cluster.sync();
+  // ---- RMS norm: every CTA computes the three sums redundantly (back to front, _Expr::sum()) ----
+  if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
-    float ss = XM_FMUL(sh.norm[g][LC - 1], sh.norm[g][LC - 1]);
-    for (int i = LC - 2; i >= 0; --i) ss = XM_FADD(ss, XM_FMUL(sh.norm[g][i], sh.norm[g][i]));
+    float ss = XM_FMUL(sh.gat[g][LC - 1], sh.gat[g][LC - 1]);
+    for (int i = LC - 2; i >= 0; --i) ss = XM_FADD(ss, XM_FMUL(sh.gat[g][i], sh.gat[g][i]));
     const float iv = XM_FDIV(1.0f, __fsqrt_rn(XM_FADD(XM_FDIV(ss, (float)LC), 1e-5f)));
-    L.gate[g].ivar[e] = iv;
     sh.scal[g] = iv;
+    if (rank == 0) L.gate[g].ivar[e] = iv;
   }
   __syncthreads();
-  if (tid < 3 * LC) {
-    const int g = tid / LC, i = tid % LC;
+  if (tid < 96 && (tid & 31) < LCPC) {
+    const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
     GateState& G = L.gate[g];
-    const float n = XM_FMUL(sh.norm[g][i], sh.scal[g]);
-    G.norm[(size_t)e * LC + i] = n;
-    float s = XM_FADD(XM_FMUL(n, G.gamma[i]), G.beta[i]);
+    const float n = XM_FMUL(sh.gat[g][cell], sh.scal[g]);
+    G.norm[(size_t)e * LC + cell] = n;
+    float s = XM_FADD(XM_FMUL(n, G.gamma[cell]), G.beta[cell]);
     s = (g == 1) ? xm_tanhf(s) : xm_logistic(s);
-    G.state[(size_t)e * LC + i] = s;
+    G.state[(size_t)e * LC + cell] = s;
     sh.act[g][i] = s;
   }
   __syncthreads();
-  if (tid < LC) {
-    const int i = tid;
+  if (tid < LCPC) {
+    const int i = tid, cell = LCPC * rank + i;
     const float fs = sh.act[0][i], gs = sh.act[1][i], os = sh.act[2][i];
-    float c = L.state[i];
-    L.last_state[(size_t)e * LC + i] = c;
+    float c = L.state[cell];
+    L.last_state[(size_t)e * LC + cell] = c;
     const float ig = XM_FSUB(1.0f, fs);
-    L.input_gate_state[(size_t)e * LC + i] = ig;
+    L.input_gate_state[(size_t)e * LC + cell] = ig;
     c = XM_FMUL(c, fs);
     c = XM_FADD(c, XM_FMUL(gs, ig));
-    L.state[i] = c;
+    L.state[cell] = c;
     const float ts = xm_tanhf(c);
-    L.tanh_state[(size_t)e * LC + i] = ts;
-    hidden_out[i] = XM_FMUL(os, ts);
+    L.tanh_state[(size_t)e * LC + cell] = ts;
+    const float h = XM_FMUL(os, ts);
+    S.hidden[l * LC + cell] = h;
+#pragma unroll
+    for (int cc = 0; cc < LSTM_CTAS; ++cc) {
+      float* rh = cluster.map_shared_rank(sh.hid, cc);
+      rh[l * LC + cell] = h;
+    }
   }
-  __syncthreads();
-  if (tid == 0) { L.epoch = (e + 1 == LH) ? 0 : e + 1; }
-  __syncthreads();
+  if (rank == 0 && tid == 0) L.epoch = (e + 1 == LH) ? 0 : e + 1;
+  cluster.sync();
 }
 
 // Lstm::Predict (lstm.cpp:120-150)
-__device__ void lstm_predict(LstmState& S, unsigned input, LstmShared& sh, int tid) {
+__device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned input, LstmShared& sh, int rank, int tid) {
   const int V = S.V, e = S.epoch, HW = LSTM_HID;
   for (int l = 0; l < 2; ++l) {
     LayerState& L = S.layer[l];
-    float* in = L.input + (size_t)e * L.in_size;
-    if (tid < LC) in[V + tid] = S.hidden[l * LC + tid];
-    __syncthreads();
-    lstm_layer_forward(L, V, (int)input, &S.hidden[l * LC], sh, tid);
-    if (l == 0) {
-      float* in1 = S.layer[1].input + (size_t)e * S.layer[1].in_size;
-      if (tid < LC) in1[V + LC + tid] = S.hidden[tid];
-      __syncthreads();
+    float* in = L.input + (size_t)L.epoch * L.in_size;
+    // own h(t-1) into [V, V+200); layer 1 also gets layer 0's new h into [V+200, V+400)
+    if (rank == 0) {
+      if (tid < LC) in[V + tid] = sh.hid[l * LC + tid];
+      if (l == 1 && tid >= 256 && tid < 256 + LC) in[V + LC + (tid - 256)] = sh.hid[tid - 256];
     }
+    __threadfence();
+    cluster.sync();
+    lstm_layer_forward(cluster, S, l, (int)input, sh, rank, tid);
   }
-  for (int j = tid; j < HW; j += LSTM_THREADS) sh.in[j] = S.hidden[j];
-  __syncthreads();
-  float* out = S.output + (size_t)e * V;
+  // ---- softmax layer: this CTA's rows of W_o[e] from HBM/L2 into shared memory, then 32 chains ----
+  const int rpc = (V + LSTM_CTAS - 1) / LSTM_CTAS;                  // rows per CTA
+  const int r0 = rank * rpc, r1 = min(V, r0 + rpc);
   const float* W = S.out_w + (size_t)e * V * HW;
-  float sum = 0.0f;
-  if (tid < V) {
-    const float* wr = W + (size_t)tid * HW;
+  const int nrow = max(0, r1 - r0);
+  for (int k = tid; k < nrow * HW; k += LSTM_THREADS) lcp_async4(sh.pool + k, W + (size_t)r0 * HW + k);
+  lcp_async_wait();
+  __syncthreads();
+  if (tid < nrow) {
+    const float* wr = sh.pool + (size_t)tid * HW;
+    float sum = 0.0f;
 #pragma unroll 4
-    for (int j = 0; j < HW; ++j) sum = XM_FADD(sum, XM_FMUL(sh.in[j], wr[j]));
-    sh.out[tid] = sum;
+    for (int j = 0; j < HW; ++j) sum = XM_FADD(sum, XM_FMUL(sh.hid[j], wr[j]));
+#pragma unroll
+    for (int c = 0; c < LSTM_CTAS; ++c) { float* rl = cluster.map_shared_rank(sh.logits, c); rl[r0 + tid] = sum; }
   }
-  // max_out = max(0, max_i sum_i): order-independent
-  float mx = (tid < V) ? sum : 0.0f;
-  mx = fmaxf(mx, 0.0f);
+  cluster.sync();
+  // every CTA: max(0, max_i), exp, front-to-back total, divide (identical results everywhere)
+  float mx = 0.0f;
+  for (int i = tid; i < V; i += LSTM_THREADS) mx = fmaxf(mx, sh.logits[i]);
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) sh.red[tid >> 5] = mx;
+  if ((tid & 31) == 0) sh.err[tid >> 5] = mx;
   __syncthreads();
-  if (tid < 32) {
-    float m2 = sh.red[tid];
-    for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-    if (tid == 0) sh.scal[0] = m2;
+  if (tid == 0) { float m2 = 0.0f; for (int w = 0; w < LSTM_THREADS / 32; ++w) m2 = fmaxf(m2, sh.err[w]); sh.scal[4] = m2; }
+  __syncthreads();
+  const float max_out = sh.scal[4];
+  for (int i = tid; i < V; i += LSTM_THREADS) sh.logits[i] = xm_expf(XM_FSUB(sh.logits[i], max_out));
+  __syncthreads();
+  if (tid == 0) {
+    float total = sh.logits[0];
+    for (int i = 1; i < V; ++i) total = XM_FADD(total, sh.logits[i]);
+    sh.scal[5] = total;
   }
   __syncthreads();
-  const float max_out = sh.scal[0];
-  if (tid < V) sh.out[tid] = xm_expf(XM_FSUB(sh.out[tid], max_out));
-  __syncthreads();
-  if (tid == 0) {                      // valarray::sum(): front to back
-    float total = sh.out[0];
-    for (int i = 1; i < V; ++i) total = XM_FADD(total, sh.out[i]);
-    sh.scal[1] = total;
+  for (int i = tid; i < V; i += LSTM_THREADS) {
+    const float o = XM_FDIV(sh.logits[i], sh.scal[5]);
+    sh.logits[i] = o;
+    if (rank == 0) S.output[(size_t)e * V + i] = o;
   }
-  __syncthreads();
-  if (tid < V) { const float o = XM_FDIV(sh.out[tid], sh.scal[1]); sh.out[tid] = o; out[tid] = o; }
-  __syncthreads();
-  if (tid == 0) S.epoch = (e + 1 == LH) ? 0 : e + 1;
-  __syncthreads();
+  if (rank == 0 && tid == 0) S.epoch = (e + 1 == LH) ? 0 : e + 1;
+  __threadfence();
+  cluster.sync();
 }
 
 // One (epoch, layer) step of the error recursion (LstmLayer::BackwardPass, lstm-layer.cpp:108-197)
-// WITHOUT the weight-gradient accumulation and Adam, which lstm_apply_updates() does afterwards.
-__device__ void lstm_layer_backward(LstmState& S, int l, int ep, LstmShared& sh, int tid,
-                                    float* gamma_u, float* beta_u) {
+// WITHOUT the weight-gradient accumulation and Adam (lstm_apply_updates does those afterwards).
+// `rec` = this CTA's slice of the recurrent weight blocks, staged once per BPTT:
+//   rec[((g*ntypes + type)*LC + j)*LCPC + i] = W_g(cell j, column 2V + type*200 + (25*rank + i)), ntypes = l + 1
+__device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, int l, int ep, LstmShared& sh, const float* rec,
+                                    int rank, int tid, float* gamma_u, float* beta_u, float* he_reg, float* stored_reg, float* se_reg) {
   LayerState& L = S.layer[l];
-  const int V = S.V;
   const float kClip = 10.0f;
   float he = 0.0f, stored = 0.0f, se = 0.0f;
-  if (tid < LC) {
-    const int i = tid;
-    const size_t o = (size_t)ep * LC + i;
+  if (tid < LCPC) {
+    const int i = tid, cell = LCPC * rank + i;
+    const size_t o = (size_t)ep * LC + cell;
     const float ts = L.tanh_state[o], os = L.gate[2].state[o], gs = L.gate[1].state[o], fs = L.gate[0].state[o];
     const float ig = L.input_gate_state[o], ls = L.last_state[o];
-    he = S.hidden_error[i];
+    he = *he_reg;
     if (ep == LH - 1) { stored = he; se = 0.0f; }
-    else { stored = XM_FADD(L.stored_error[i], he); se = L.state_error[i]; }
-    sh.e[2][i] = XM_FMUL(XM_FMUL(XM_FMUL(ts, stored), os), XM_FSUB(1.0f, os));
+    else { stored = XM_FADD(*stored_reg, he); se = *se_reg; }
+    sh.eown[2][i] = XM_FMUL(XM_FMUL(XM_FMUL(ts, stored), os), XM_FSUB(1.0f, os));
     se = XM_FADD(se, XM_FMUL(XM_FMUL(stored, os), XM_FSUB(1.0f, XM_FMUL(ts, ts))));
-    sh.e[1][i] = XM_FMUL(XM_FMUL(se, ig), XM_FSUB(1.0f, XM_FMUL(gs, gs)));
-    sh.e[0][i] = XM_FMUL(XM_FMUL(XM_FMUL(XM_FSUB(ls, gs), se), fs), ig);
+    sh.eown[1][i] = XM_FMUL(XM_FMUL(se, ig), XM_FSUB(1.0f, XM_FMUL(gs, gs)));
+    sh.eown[0][i] = XM_FMUL(XM_FMUL(XM_FMUL(XM_FSUB(ls, gs), se), fs), ig);
     he = 0.0f;
     if (ep > 0) { se = XM_FMUL(se, fs); stored = 0.0f; }
   }
-  if (tid == 0 && ep == 0) { if (L.update_steps < 3000) ++L.update_steps; }
+  if (rank == 0 && tid == 0 && ep == 0) { if (L.update_steps < 3000) ++L.update_steps; }
   __syncthreads();
-  // per gate: beta_u/gamma_u accumulation, RMS-norm backward
-  if (tid < 3 * LC) {
-    const int g = tid / LC, i = tid % LC;
+  // per gate: beta_u/gamma_u accumulation, scale by gamma*ivar, all-gather for the RMS-norm backward sum
+  float escaled = 0.0f;
+  if (tid < 96 && (tid & 31) < LCPC) {
+    const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
     GateState& G = L.gate[g];
-    const float n = G.norm[(size_t)ep * LC + i];
-    float e = sh.e[g][i];
+    const float n = G.norm[(size_t)ep * LC + cell];
+    float e = sh.eown[g][i];
     if (ep == LH - 1) { *gamma_u = 0.0f; *beta_u = 0.0f; }
     *beta_u = XM_FADD(*beta_u, e);
     *gamma_u = XM_FADD(*gamma_u, XM_FMUL(e, n));
-    e = XM_FMUL(e, XM_FMUL(G.gamma[i], G.ivar[ep]));
-    sh.e[g][i] = e;
-    sh.norm[g][i] = n;
+    escaled = XM_FMUL(e, XM_FMUL(G.gamma[cell], G.ivar[ep]));
+    sh.nown[g][i] = n;
+#pragma unroll
+    for (int c = 0; c < LSTM_CTAS; ++c) {
+      float (*rd)[LC] = cluster.map_shared_rank(sh.gat, c);
+      rd[g][cell] = escaled;
+    }
   }
-  __syncthreads();
+  // the full norm vector of this step (for the sum) straight from HBM/L2 into shared memory
+  for (int k = tid; k < 3 * LC; k += LSTM_THREADS) sh.gat2[k / LC][k % LC] = L.gate[k / LC].norm[(size_t)ep * LC + (k % LC)];
+  cluster.sync();
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
-    float s = XM_FMUL(sh.e[g][LC - 1], sh.norm[g][LC - 1]);
-    for (int i = LC - 2; i >= 0; --i) s = XM_FADD(s, XM_FMUL(sh.e[g][i], sh.norm[g][i]));
+    float s = XM_FMUL(sh.gat[g][LC - 1], sh.gat2[g][LC - 1]);
+    for (int i = LC - 2; i >= 0; --i) s = XM_FADD(s, XM_FMUL(sh.gat[g][i], sh.gat2[g][i]));
     sh.scal[g] = XM_FDIV(s, (float)LC);
   }
   __syncthreads();
-  if (tid < 3 * LC) {
-    const int g = tid / LC, i = tid % LC;
-    const float e = XM_FSUB(sh.e[g][i], XM_FMUL(sh.scal[g], sh.norm[g][i]));
-    sh.act[g][i] = e;                                   // final gate error for this step
-    L.gate[g].err[(size_t)ep * LC + i] = e;
+  cluster.sync();                       // everyone finished reading gat/gat2 before they are overwritten
+  if (tid < 96 && (tid & 31) < LCPC) {
+    const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
+    const float e = XM_FSUB(escaled, XM_FMUL(sh.scal[g], sh.nown[g][i]));
+    L.gate[g].err[(size_t)ep * LC + cell] = e;       // final gate error of this step
+#pragma unroll
+    for (int c = 0; c < LSTM_CTAS; ++c) {
+      float (*rd)[LC] = cluster.map_shared_rank(sh.gat2, c);
+      rd[g][cell] = e;
+    }
+  }
+  cluster.sync();
+  // transposed mat-vecs for the own 25 columns: hidden_error (layer below) and stored_error (previous step)
+  float f1 = 0.0f, f2 = 0.0f;
+  if (tid < 192 && (tid & 31) < LCPC) {
+    const int wv = tid >> 5, g = wv >> 1, type = wv & 1, i = tid & 31;    // 6 warps: (gate, type)
+    const bool need = type == 1 ? (l > 0) : (ep > 0);
+    if (need) {
+      const int ntypes = l + 1;
+      const float* w = rec + ((size_t)(g * ntypes + type) * LC) * LCPC + i;
+      float f = 0.0f;
+#pragma unroll 8
+      for (int j = 0; j < LC; ++j) f = XM_FADD(f, XM_FMUL(sh.gat2[g][j], w[(size_t)j * LCPC]));
+      sh.pool[LSTM_POOL_FLOATS - 256 + wv * 32 + i] = f;
+    } else {
+      sh.pool[LSTM_POOL_FLOATS - 256 + wv * 32 + i] = 0.0f;
+    }
   }
   __syncthreads();
-  // transposed mat-vecs: hidden_error (to the layer below) and stored_error (to the previous step)
-  if (tid < 3 * LC) {
-    const int g = tid / LC, i = tid % LC;
-    const float* w = L.gate[g].w;
-    float f1 = 0.0f, f2 = 0.0f;
-    if (l > 0) {
-      const float* col = w + (size_t)(2 * V + LC + i) * LC;
-#pragma unroll 8
-      for (int j = 0; j < LC; ++j) f1 = XM_FADD(f1, XM_FMUL(sh.act[g][j], col[j]));
-    }
-    if (ep > 0) {
-      const float* col = w + (size_t)(2 * V + i) * LC;
-#pragma unroll 8
-      for (int j = 0; j < LC; ++j) f2 = XM_FADD(f2, XM_FMUL(sh.act[g][j], col[j]));
-    }
-    sh.tmp[g][i] = f1;
-    sh.tmp2[g][i] = f2;
-  }
-  __syncthreads();
-  if (tid < LC) {
+  if (tid < LCPC) {
     const int i = tid;
-    if (l > 0) { he = XM_FADD(he, sh.tmp[0][i]); he = XM_FADD(he, sh.tmp[1][i]); he = XM_FADD(he, sh.tmp[2][i]); }
-    if (ep > 0) { stored = XM_FADD(stored, sh.tmp2[0][i]); stored = XM_FADD(stored, sh.tmp2[1][i]); stored = XM_FADD(stored, sh.tmp2[2][i]); }
-    L.state_error[i] = clipf(se, kClip);
-    L.stored_error[i] = clipf(stored, kClip);
-    S.hidden_error[i] = clipf(he, kClip);
+    const float* sc = sh.pool + LSTM_POOL_FLOATS - 256;
+    if (l > 0) { f1 = sc[1 * 32 + i]; he = XM_FADD(he, f1); f1 = sc[3 * 32 + i]; he = XM_FADD(he, f1); f1 = sc[5 * 32 + i]; he = XM_FADD(he, f1); }
+    if (ep > 0) { f2 = sc[0 * 32 + i]; stored = XM_FADD(stored, f2); f2 = sc[2 * 32 + i]; stored = XM_FADD(stored, f2); f2 = sc[4 * 32 + i]; stored = XM_FADD(stored, f2); }
+    *se_reg = clipf(se, kClip);
+    *stored_reg = clipf(stored, kClip);
+    *he_reg = clipf(he, kClip);
   }
   __syncthreads();
 }
 
 // Weight-gradient accumulation in the reference's time order + Adam (lstm-layer.cpp:11-32,182-196).
-__device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int tid, float gamma_u[2], float beta_u[2]) {
+// Each CTA owns its 25 cells: gate errors of all 100 steps in shared memory, inputs tiled by column.
+__device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int tid, const float* gamma_u, const float* beta_u) {
   const int V = S.V;
   const float beta1 = 0.025f, beta2 = 0.9999f, eps = 1e-6f;
+  enum { TILE = 128 };
+  float* err_s = sh.pool;                         // [3][LH][LCPC]
+  float* in_t = sh.pool + 3 * LH * LCPC;          // [LH][TILE]
   for (int l = 0; l < 2; ++l) {
     LayerState& L = S.layer[l];
     const float* ad = S.adam + 4 * L.update_steps;
     const float alpha = ad[0], bc1 = ad[1], bc2 = ad[2];
-    const int in_size = L.in_size;
-    for (int g = 0; g < 3; ++g) {
-      GateState& G = L.gate[g];
-      const size_t n = (size_t)G.row * LC;
-      for (size_t idx = tid; idx < n; idx += LSTM_THREADS) {
-        const int col = (int)(idx / LC), i = (int)(idx % LC);
+    const int in_size = L.in_size, row = in_size + V;
+    __syncthreads();
+    for (int k = tid; k < 3 * LH * LCPC; k += LSTM_THREADS) {
+      const int g = k / (LH * LCPC), r = k - g * LH * LCPC, ep = r / LCPC, i = r - ep * LCPC;
+      err_s[k] = L.gate[g].err[(size_t)ep * LC + LCPC * rank + i];
+    }
+    for (int c0 = 0; c0 < row; c0 += TILE) {
+      const int nc = min(TILE, row - c0);
+      __syncthreads();
+      // dense columns of this tile: inputs of all 100 steps
+      for (int k = tid; k < LH * TILE; k += LSTM_THREADS) {
+        const int ep = k / TILE, c = k - ep * TILE, col = c0 + c;
+        in_t[k] = (c < nc && col >= V) ? L.input[(size_t)ep * in_size + (col - V)] : 0.0f;
+      }
+      __syncthreads();
+      for (int k = tid; k < 3 * nc * LCPC; k += LSTM_THREADS) {
+        const int g = k / (nc * LCPC), r = k - g * nc * LCPC, c = r / LCPC, i = r - c * LCPC, col = c0 + c;
+        const float* es = err_s + (size_t)g * LH * LCPC + i;
         float acc = 0.0f;
         if (col >= V) {
-          const float* in = L.input + (col - V);
-          for (int ep = LH - 1; ep >= 0; --ep)
-            acc = XM_FADD(acc, XM_FMUL(G.err[(size_t)ep * LC + i], in[(size_t)ep * in_size]));
+          for (int ep = LH - 1; ep >= 0; --ep) acc = XM_FADD(acc, XM_FMUL(es[ep * LCPC], in_t[ep * TILE + c]));
         } else {
-          for (int ep = LH - 1; ep >= 0; --ep)
-            if (sh.sym[ep] == col) acc = XM_FADD(acc, G.err[(size_t)ep * LC + i]);
+          for (int ep = LH - 1; ep >= 0; --ep) if (sh.sym[ep] == col) acc = XM_FADD(acc, es[ep * LCPC]);
         }
+        GateState& G = L.gate[g];
+        const size_t idx = ((size_t)rank * row + col) * LCPC + i;
         float m = G.m[idx], v = G.v[idx], w = G.w[idx];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
@@ -266,95 +370,131 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int tid, float 
         G.m[idx] = m; G.v[idx] = v; G.w[idx] = w;
       }
     }
-    if (tid < 3 * LC) {
-      const int g = tid / LC, i = tid % LC;
+    if (tid < 96 && (tid & 31) < LCPC) {
+      const int g = tid >> 5, cell = LCPC * rank + (tid & 31);
       GateState& G = L.gate[g];
       {
         const float acc = gamma_u[l];
-        float m = G.gamma_m[i], v = G.gamma_v[i], w = G.gamma[i];
+        float m = G.gamma_m[cell], v = G.gamma_v[cell], w = G.gamma[cell];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
         w = XM_FSUB(w, XM_FMUL(alpha, XM_FDIV(XM_FDIV(m, bc1), __fsqrt_rn(XM_FADD(XM_FDIV(v, bc2), eps)))));
-        G.gamma_m[i] = m; G.gamma_v[i] = v; G.gamma[i] = w;
+        G.gamma_m[cell] = m; G.gamma_v[cell] = v; G.gamma[cell] = w;
       }
       {
         const float acc = beta_u[l];
-        float m = G.beta_m[i], v = G.beta_v[i], w = G.beta[i];
+        float m = G.beta_m[cell], v = G.beta_v[cell], w = G.beta[cell];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
         w = XM_FSUB(w, XM_FMUL(alpha, XM_FDIV(XM_FDIV(m, bc1), __fsqrt_rn(XM_FADD(XM_FDIV(v, bc2), eps)))));
-        G.beta_m[i] = m; G.beta_v[i] = v; G.beta[i] = w;
+        G.beta_m[cell] = m; G.beta_v[cell] = v; G.beta[cell] = w;
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 // ByteMixer::ByteUpdate -> Lstm::SetInput + Lstm::Perceive + Lstm::Predict (byte-mixer.cpp:22-38,
-// lstm.cpp:80-150). `ppmd` = 256-entry PPMD distribution after this byte (or null), `byte` = the
-// byte just completed. Leaves the new 256-entry distribution in S.bm.probs.
-__device__ void lstm_byte_update(LstmState& S, const float* ppmd, u32 byte, LstmShared& sh, int tid) {
+// lstm.cpp:80-150) by the whole cluster. `ppmd` = 256-entry PPMD distribution after this byte (or
+// null), `byte` = the byte just completed. Leaves the new 256-entry distribution in S.bm.probs.
+__device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, const float* ppmd, u32 byte, LstmShared& sh, int rank, int tid) {
   const int V = S.V, HW = LSTM_HID;
   const unsigned input = (unsigned)S.byte_map[byte];
-  // SetInput: aux[k] = 2 * ppmd[k-th vocabulary byte] into both layers' input at epoch_
-  if (tid < 256 && S.vocab[tid]) {
-    const float p = ppmd ? ppmd[tid] : (float)(1. / 256);
-    const float a = XM_FMUL(XM_FADD(0.0f, p), 2.0f);
-    const int k = S.byte_map[tid];
-    S.layer[0].input[(size_t)S.epoch * S.layer[0].in_size + k] = a;
-    S.layer[1].input[(size_t)S.epoch * S.layer[1].in_size + k] = a;
-  }
-  __syncthreads();
   const int epoch = S.epoch;
   const int last_epoch = epoch == 0 ? LH - 1 : epoch - 1;
   const int old_input = (int)S.input_history[last_epoch];
-  __syncthreads();
-  if (tid == 0) S.input_history[last_epoch] = input;
-  __syncthreads();
+  // hidden vector of the previous step, everywhere
+  for (int j = tid; j < HW; j += LSTM_THREADS) sh.hid[j] = S.hidden[j];
+  // SetInput: aux[k] = 2 * ppmd[k-th vocabulary byte] into both layers' input at epoch_
+  if (rank == 0 && tid < 256 && S.vocab[tid]) {
+    const float p = ppmd ? ppmd[tid] : (float)(1. / 256);
+    const float a = XM_FMUL(XM_FADD(0.0f, p), 2.0f);
+    const int k = S.byte_map[tid];
+    S.layer[0].input[(size_t)epoch * S.layer[0].in_size + k] = a;
+    S.layer[1].input[(size_t)epoch * S.layer[1].in_size + k] = a;
+  }
+  __threadfence();
+  cluster.sync();
+  if (rank == 0 && tid == 0) S.input_history[last_epoch] = input;
+  __threadfence();
+  cluster.sync();
   if (epoch == 0) {
-    // input symbol of step ep is input_history[ep-1]; for ep == 0 the value that was just overwritten
+    // ------------------------------ truncated BPTT ------------------------------
     if (tid < LH) sh.sym[tid] = tid == 0 ? old_input : (int)S.input_history[tid - 1];
     float gamma_u[2] = {0.0f, 0.0f}, beta_u[2] = {0.0f, 0.0f};
+    float he_reg = 0.0f, stored_reg[2] = {0.0f, 0.0f}, se_reg[2] = {0.0f, 0.0f};
+    if (tid < LCPC) he_reg = S.hidden_error[LCPC * rank + tid];
+    // recurrent weight blocks of both layers (constant during the BPTT) into shared memory
+    float* rec[2];
+    rec[0] = sh.pool;                                   // layer 0: [3][1][LC][LCPC]
+    rec[1] = sh.pool + 3 * 1 * LC * LCPC;               // layer 1: [3][2][LC][LCPC]
+    float* wo_s = sh.pool + 3 * 3 * LC * LCPC;          // [V][LCPC] slice of W_o[ep] for the current layer
+    for (int l = 0; l < 2; ++l) {
+      const int row = S.layer[l].in_size + V;
+      const int ntypes = l + 1;                         // layer 0 has no layer below: only the stored_error block
+      for (int k = tid; k < 3 * ntypes * LC * LCPC; k += LSTM_THREADS) {
+        const int i = k % LCPC, j = (k / LCPC) % LC, type = (k / (LCPC * LC)) % ntypes, g = k / (LCPC * LC * ntypes);
+        const int col = 2 * V + type * LC + LCPC * rank + i;
+        lcp_async4(rec[l] + k, S.layer[l].gate[g].w + lstm_widx(row, col, j));
+      }
+    }
+    lcp_async_wait();
     __syncthreads();
     for (int ep = LH - 1; ep >= 0; --ep) {
       const float* out = S.output + (size_t)ep * V;
       const float* W = S.out_w + (size_t)ep * V * HW;
-      if (tid < V) sh.err[tid] = ((unsigned)tid == S.input_history[ep]) ? XM_FSUB(out[tid], 1.0f) : out[tid];
-      __syncthreads();
+      for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = ((unsigned)i == S.input_history[ep]) ? XM_FSUB(out[i], 1.0f) : out[i];
       for (int l = 1; l >= 0; --l) {
-        if (tid < LC) {
-          float he = S.hidden_error[tid];
-          const float* wc = W + l * LC + tid;
-#pragma unroll 4
-          for (int i = 0; i < V; ++i) he = XM_FADD(he, XM_FMUL(wc[(size_t)i * HW], sh.err[i]));
-          S.hidden_error[tid] = he;
-        }
+        // slice of W_o[ep]: columns l*200 + own 25 cells, all V rows
         __syncthreads();
-        lstm_layer_backward(S, l, ep, sh, tid, &gamma_u[l], &beta_u[l]);
+        for (int k = tid; k < V * LCPC; k += LSTM_THREADS) {
+          const int i = k / LCPC, jj = k - i * LCPC;
+          lcp_async4(wo_s + k, W + (size_t)i * HW + l * LC + LCPC * rank + jj);
+        }
+        lcp_async_wait();
+        __syncthreads();
+        if (tid < LCPC) {
+          float he = he_reg;
+          const float* wc = wo_s + tid;
+#pragma unroll 4
+          for (int i = 0; i < V; ++i) he = XM_FADD(he, XM_FMUL(wc[(size_t)i * LCPC], sh.err[i]));
+          he_reg = he;
+        }
+        lstm_layer_backward(cluster, S, l, ep, sh, rec[l], rank, tid, &gamma_u[l], &beta_u[l], &he_reg, &stored_reg[l], &se_reg[l]);
       }
     }
-    lstm_apply_updates(S, sh, tid, gamma_u, beta_u);
+    if (tid < LCPC) {
+      const int cell = LCPC * rank + tid;
+      S.hidden_error[cell] = he_reg;
+      for (int l = 0; l < 2; ++l) { S.layer[l].stored_error[cell] = stored_reg[l]; S.layer[l].state_error[cell] = se_reg[l]; }
+    }
+    lstm_apply_updates(S, sh, rank, tid, gamma_u, beta_u);
+    __threadfence();
+    cluster.sync();
   }
-  // output layer SGD (lstm.cpp:112-116): copy W_o[last_epoch] to W_o[epoch] with the step applied
+  // ---- output layer SGD (lstm.cpp:112-116): W_o[epoch] = W_o[last_epoch] - (lr*err_i) * hidden, own rows ----
   {
+    const int rpc = (V + LSTM_CTAS - 1) / LSTM_CTAS;
+    const int r0 = rank * rpc, r1 = min(V, r0 + rpc);
     const float* out = S.output + (size_t)last_epoch * V;
     const float* Wl = S.out_w + (size_t)last_epoch * V * HW;
     float* We = S.out_w + (size_t)epoch * V * HW;
-    for (int j = tid; j < HW; j += LSTM_THREADS) sh.in[j] = S.hidden[j];
-    if (tid < V) sh.err[tid] = XM_FMUL(0.03f, ((unsigned)tid == input) ? XM_FSUB(out[tid], 1.0f) : out[tid]);
+    for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = XM_FMUL(0.03f, ((unsigned)i == input) ? XM_FSUB(out[i], 1.0f) : out[i]);
     __syncthreads();
-    const int n = V * HW;
-    for (int idx = tid; idx < n; idx += LSTM_THREADS) {
+    for (int idx = r0 * HW + tid; idx < r1 * HW; idx += LSTM_THREADS) {
       const int i = idx / HW, j = idx - i * HW;
-      We[idx] = XM_FSUB(Wl[idx], XM_FMUL(sh.err[i], sh.in[j]));
+      We[idx] = XM_FSUB(Wl[idx], XM_FMUL(sh.err[i], sh.hid[j]));
     }
     __syncthreads();
   }
-  lstm_predict(S, input, sh, tid);
+  lstm_predict(cluster, S, input, sh, rank, tid);
   // ByteMixer: scatter back to 256 bytes; ByteModel::ByteUpdate resets the range
-  if (tid < 256) S.bm.probs[tid] = S.vocab[tid] ? sh.out[S.byte_map[tid]] : 0.0f;
-  if (tid == 0) { S.bm.top = 255; S.bm.bot = 0; }
-  __syncthreads();
+  if (rank == 0) {
+    if (tid < 256) S.bm.probs[tid] = S.vocab[tid] ? sh.logits[S.byte_map[tid]] : 0.0f;
+    if (tid == 0) { S.bm.top = 255; S.bm.bot = 0; }
+  }
+  __threadfence();
+  cluster.sync();
 }
 
 // Bit-level read-out of the byte distribution (ByteModel::Predict + the override test of
@@ -369,24 +509,27 @@ __device__ void bm_perceive(ByteModelState& b, int bit) {
   if (bit) b.bot = b.mid + 1; else b.top = b.mid;
 }
 
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
+__global__ void __cluster_dims__(LSTM_CTAS, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
-  const ChunkArgs a = args_all[blockIdx.x];
+  cgl::cluster_group cluster = cgl::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const ChunkArgs a = args_all[blockIdx.x / LSTM_CTAS];
   LstmState& S = a.st->lstm;
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
   const int tid = threadIdx.x;
   for (u32 pos = 0; pos < a.n_bytes; ++pos) {
     const u32 byte = a.bytes[pos];
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
       for (int j = 7; j >= 0; --j) {
         const u64 t = (u64)pos * 8 + (7 - j);
         lstm_readout(S, T, &a.lstm_x[2 * t], &a.lstm_x[2 * t + 1]);
         bm_perceive(S.bm, (byte >> j) & 1);
       }
     }
-    __syncthreads();
-    lstm_byte_update(S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, tid);
+    __threadfence();
+    cluster.sync();
+    lstm_byte_update(cluster, S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, rank, tid);
   }
 }
 
@@ -394,13 +537,15 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
 __global__ void lstm_predict_kernel(StreamState* st, Tables T) {
   if (threadIdx.x == 0) lstm_readout(st->lstm, T, &st->lstm_x, &st->lstm_override);
 }
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_perceive_kernel(StreamState* st, int bit, int byte_done, u32 byte, const float* ppmd) {
-  extern __shared__ unsigned char smem_raw[];
-  LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
+__global__ void lstm_bit_kernel(StreamState* st, int bit) {
   if (threadIdx.x == 0) bm_perceive(st->lstm.bm, bit);
-  __syncthreads();
-  if (byte_done) lstm_byte_update(st->lstm, ppmd, byte, sh, threadIdx.x);
+}
+__global__ void __cluster_dims__(LSTM_CTAS, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd) {
+  cgl::cluster_group cluster = cgl::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
+  lstm_byte_update(cluster, st->lstm, ppmd, byte, sh, (int)cluster.block_rank(), threadIdx.x);
 }
 
 #undef LC

@@ -97,8 +97,8 @@ struct SmallState {
 
 // ---- LSTM byte mixer (reference mixer/lstm.cpp, lstm-layer.cpp, byte-mixer.cpp) ----
 struct GateState {
-  float* w;        // [row][C]   TRANSPOSED: column-major over cells so that 200 consecutive
-                   //            threads (cells) read 200 consecutive floats
+  float* w;        // [8][row][25] cell-block-major (lstm_widx): the 25 cells owned by one CTA of the
+                   //              LSTM cluster are contiguous for every column
   float* m; float* v;           // Adam moments, same layout
   float* state; float* norm;    // [H][C]
   float* err;                   // [H][C] post-normalisation gate error of every BPTT step
