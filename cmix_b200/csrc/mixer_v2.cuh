@@ -26,9 +26,9 @@
 namespace cmixb200 {
 
 // Warp roles. The SM's 4 schedulers own warps (w % 4); the arbiter prefers the highest warp id,
-// so the latency-critical chain warp is the LAST warp and no mover shares its scheduler
-// (warps 3, 7, 11 stay parked at the final barrier).
-enum { V2_NBUF = 20, V2_RING = 4, V2_M_WARPS = 11, V2_M_THREADS = V2_M_WARPS * 32, V2_CM_THREADS = V2_M_THREADS + 32,
+// so the latency-critical chain warp (15) and the tail warp (14) each get a scheduler of their own:
+// movers are the warps with (w % 4) < 2; warps 2, 3, 6, 7, 10, 11 stay parked at the final barrier.
+enum { V2_NBUF = 20, V2_RING = 4, V2_M_WARPS = 8, V2_M_THREADS = V2_M_WARPS * 32, V2_CM_THREADS = V2_M_THREADS + 32,
        V2_C_WARP = 15, V2_T_WARP = 14 };
 
 struct RowJob { int buf; int mixer; u32 load_slot; u32 evict_slot; int do_evict; int do_load; };
@@ -45,16 +45,17 @@ struct MixShared2 {
   float extras[2][N_L0 + 6];                 // clamped layer-0 outputs of bit parity (update snapshot)
   u32 sel[2][SEL_PITCH];
   // CTA1 only: clamped outputs of mixers 0..12 received from CTA0
-  float ring_in[V2_RING][16]; volatile u32 ring_in_seq[V2_RING];
+  alignas(8) uint2 ring_in[V2_RING][16];      // {float bits, sequence}: value and flag travel in ONE 8-byte store
   volatile u32 peer_progress;                // CTA0 only: bits CTA1 has consumed from ring_in
   // CTA0 only: ring feeding the T warp
-  float ring_t[V2_RING][32]; volatile u32 ring_t_seq_a[V2_RING]; volatile u32 ring_t_seq_b[V2_RING];
+  alignas(8) uint2 ring_t[V2_RING][32];
   volatile u32 t_consumed;                   // both CTAs: bits the T warp has finished
   // T warp scratch
   float in1[L1_IN + 3], in2[L2_IN + 3];
   alignas(16) float l1row[N_L1][ROW_PITCH_L1]; alignas(16) float l2row[ROW_PITCH_L2];
   float l1extra[N_L1 + 4]; float mixp1[N_L1 + 4];
   u32 slot1[N_L1 + 4];
+  alignas(8) unsigned long long row_bar; u32 row_bar_phase;   // mbarrier the row loads complete on
   float lut12[4100];                          // stretch LUT of the 12-bit replayed codes (+0.5 at 4096)
 };
 
@@ -65,8 +66,27 @@ __device__ __forceinline__ void spin_until_ge(volatile u32* p, u32 v) {
   while (*p < v) { }
 }
 
+// "LL" message slots (as in NCCL's low-latency protocol): a float and its sequence number are written
+// with one 8-byte store, so the consumer needs no fence - it polls the slot until the sequence matches.
+// (A cluster-scope fence costs an L1 invalidate + a drain of the warp's outstanding global stores.)
+__device__ __forceinline__ void ll_store(uint2* slot, float v, u32 seq) {
+  *reinterpret_cast<volatile unsigned long long*>(slot) = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+}
+__device__ __forceinline__ float ll_wait(const uint2* slot, u32 seq) {
+  unsigned long long m;
+  do { m = *reinterpret_cast<const volatile unsigned long long*>(slot); } while ((u32)(m >> 32) != seq);
+  return __uint_as_float((u32)m);
+}
+
 enum { BAR_READY = 1, BAR_COEFF = 2, BAR_MOVERS = 3 };
-#define V2_PROF(cond, slot) do { if (cond) { const long long now_ = clock64(); a.prof[slot] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
+// Per-phase cycle accounting (debug). BAR.SYNC does not block at issue, so a clock read placed right
+// after a barrier would capture the issue time; a dependent shared-memory load + MOV in front of the
+// clock read makes the sample wait for the barrier's release.
+#define V2_PROF(cond, slot) do { if (cond) { \
+    unsigned dummy_ = *reinterpret_cast<volatile unsigned*>(&sh.n_jobs), sink_; \
+    asm volatile("mov.u32 %0, %1;" : "=r"(sink_) : "r"(dummy_)); \
+    const long long now_ = clock64(); pacc[(slot) & 7] += (unsigned long long)(now_ - tprev) + (sink_ & 0u); tprev = now_; } } while (0)
+#define V2_PROF_DUMP(cond, base, n) do { if (cond) { for (int q_ = 0; q_ < (n); ++q_) a.prof[(base) + q_] += pacc[((base) + q_) & 7]; } } while (0)
 
 __device__ __forceinline__ bool selector_is_bit_level(int sel) {
   return sel == S_AUX || sel == S_LONGBIT || (sel >= S_BC0 && sel <= S_BC_RB1);
@@ -113,35 +133,75 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// movers: execute the row jobs (evictions first, then loads). Loads go global -> shared with
-// cp.async (LDGSTS, L1-bypassing), all in flight at once: one memory round trip per batch.
+// ---- TMA (bulk async copy) helpers: one instruction moves a whole 8.4 KB weight row ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_row(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+// movers: execute the row jobs. ONE thread drives the TMA unit (cp.async.bulk): evictions are bulk
+// stores shared->global, loads are bulk copies global->shared that complete on an mbarrier. Nothing
+// here goes through the per-thread load/store path, so the chain warp's shared-memory loads do not
+// queue behind row traffic.
 __device__ __forceinline__ void run_row_jobs(MixShared2& sh, StreamState* st, int m0, int mtid) {
   const int nj = sh.n_jobs;
-  const int per = ROW_PITCH_L0 / 4;            // 526 float4 per row
-  for (int idx = mtid; idx < nj * per; idx += V2_M_THREADS) {
-    const int j = idx / per, k = idx - j * per;
-    const RowJob jb = sh.jobs[j];
-    if (jb.do_evict) {
-      float4* g = reinterpret_cast<float4*>(st->mixer[m0 + jb.mixer].rows + (size_t)jb.evict_slot * ROW_PITCH_L0);
-      __stcg(&g[k], reinterpret_cast<const float4*>(sh.rows[jb.buf])[k]);
+  if (nj == 0) return;
+  if (mtid == 0) {
+    const unsigned bytes = ROW_PITCH_L0 * 4;
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // earlier evictions have landed in HBM/L2
+    bool any_evict = false, any_load = false;
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) { any_evict |= sh.jobs[j].do_evict != 0; any_load |= sh.jobs[j].do_load != 0; }
+    if (any_evict) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // SGD writes (generic proxy) -> visible to the TMA
+#pragma unroll 1
+      for (int j = 0; j < nj; ++j) {
+        const RowJob jb = sh.jobs[j];
+        if (jb.do_evict) tma_store_row(st->mixer[m0 + jb.mixer].rows + (size_t)jb.evict_slot * ROW_PITCH_L0, sh.rows[jb.buf], bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // sources read: the buffers may be refilled
+    }
+    if (any_load) {
+      unsigned total = 0;
+#pragma unroll 1
+      for (int j = 0; j < nj; ++j) if (sh.jobs[j].do_load) total += bytes;
+      mbar_expect_tx(&sh.row_bar, total);
+#pragma unroll 1
+      for (int j = 0; j < nj; ++j) {
+        const RowJob jb = sh.jobs[j];
+        if (jb.do_load) tma_load_row(sh.rows[jb.buf], st->mixer[m0 + jb.mixer].rows + (size_t)jb.load_slot * ROW_PITCH_L0, bytes, &sh.row_bar);
+      }
     }
   }
-  named_sync(BAR_MOVERS, V2_M_THREADS);
-  for (int idx = mtid; idx < nj * per; idx += V2_M_THREADS) {
-    const int j = idx / per, k = idx - j * per;
-    const RowJob jb = sh.jobs[j];
-    if (jb.do_load) {
-      const float4* g = reinterpret_cast<const float4*>(st->mixer[m0 + jb.mixer].rows + (size_t)jb.load_slot * ROW_PITCH_L0);
-      cp_async16(&reinterpret_cast<float4*>(sh.rows[jb.buf])[k], &g[k]);
-    }
-  }
-  if (mtid < nj) {
-    const RowJob jb = sh.jobs[mtid];
+  if (mtid >= 32 && mtid < 32 + nj) {                                  // step counters travel with their rows
+    const RowJob jb = sh.jobs[mtid - 32];
     MixerState& m = st->mixer[m0 + jb.mixer];
     if (jb.do_evict) m.row_steps[jb.evict_slot] = sh.steps[jb.buf];
     if (jb.do_load) { sh.steps[jb.buf] = m.row_steps[jb.load_slot]; sh.tag[jb.buf] = jb.load_slot; sh.dirty[jb.buf] = 0; }
   }
-  cp_async_wait_all();
+  if (mtid == 0) {
+    bool any_load = false;
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) any_load |= sh.jobs[j].do_load != 0;
+    if (any_load) { mbar_wait(&sh.row_bar, sh.row_bar_phase & 1); sh.row_bar_phase++; }
+  }
   named_sync(BAR_MOVERS, V2_M_THREADS);
 }
 
@@ -194,8 +254,10 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
       sh.swap_needed[i] = 0; sh.late[i] = 0;
     }
     for (int b = 0; b < V2_NBUF; ++b) { sh.tag[b] = 0xffffffffu; sh.dirty[b] = 0; sh.steps[b] = 0; }
-    for (int r = 0; r < V2_RING; ++r) { sh.ring_in_seq[r] = 0; sh.ring_t_seq_a[r] = 0; sh.ring_t_seq_b[r] = 0; }
-    sh.peer_progress = 0; sh.t_consumed = 0; sh.n_jobs = 0;
+    for (int r = 0; r < V2_RING; ++r) for (int k = 0; k < 32; ++k) { sh.ring_t[r][k] = make_uint2(0, 0); if (k < 16) sh.ring_in[r][k] = make_uint2(0, 0); }
+    sh.peer_progress = 0; sh.t_consumed = 0; sh.n_jobs = 0; sh.row_bar_phase = 0;
+    mbar_init(&sh.row_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int k = tid; k < 4097; k += MIX_THREADS) sh.lut12[k] = T.lut12[k];
   __syncthreads();
@@ -206,6 +268,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
     const int i = lane;                         // local mixer
     const float lr = lane < MIX_PER_CTA ? st->mixer[m0 + lane].lr : 0.0f;
     const bool pc_on = a.prof != nullptr && lane == 0; const int pb = rank == 0 ? 8 : 14;
+    unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
     for (u64 t = 0; t < n_bits; ++t) {
       const int par = (int)(t & 1), r = (int)(t & (V2_RING - 1));
@@ -223,20 +286,21 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
       float e = 0.0f, pfin = 0.0f;
       int kbase = 0;
       if (rank == 1) {
-        if (lane == 0) spin_until_ge(&sh.ring_in_seq[r], (u32)(t + 1));
+        float cin = 0.0f;
+        if (lane < MIX_PER_CTA) cin = ll_wait(&sh.ring_in[r][lane], (u32)(t + 1));
         __syncwarp();
-        fence_cluster();
-        if (lane < MIX_PER_CTA) {
-#pragma unroll
-          for (int k = 0; k < MIX_PER_CTA; ++k) e = XM_FADD(e, XM_FMUL(sh.ring_in[r][k], row[N_INPUTS + k]));
+        if (lane == 0) sh0->peer_progress = (u32)(t + 1);
+        if (lane < MIX_PER_CTA) sh.extras[par][lane] = cin;
+#pragma unroll 1
+        for (int k = 0; k < MIX_PER_CTA; ++k) {
+          const float ck = __shfl_sync(0xffffffffu, cin, k);
+          if (lane < MIX_PER_CTA) e = XM_FADD(e, XM_FMUL(ck, row[N_INPUTS + k]));
         }
-        if (lane < MIX_PER_CTA) sh.extras[par][lane] = sh.ring_in[r][lane];
-        __syncwarp();
-        if (lane == 0) { fence_cluster(); sh0->peer_progress = (u32)(t + 1); }
         kbase = MIX_PER_CTA;
       }
       V2_PROF(pc_on, pb + 2);
       float cmine = 0.0f;
+#pragma unroll 1
       for (int k = 0; k < MIX_PER_CTA; ++k) {
         if (lane == k) pfin = XM_FADD(main, e);
         const float pk = __shfl_sync(0xffffffffu, pfin, k);
@@ -264,36 +328,28 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
       V2_PROF(pc_on, pb + 4);
       // ---- publish ----
       if (rank == 0) {
-        // to CTA 1 (ring of 4; wait if it is 4 bits behind)
-        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.peer_progress, (u32)(t + 1 - V2_RING)); }
+        // to CTA 1 and to the T warp (rings of 4; wait if a consumer is 4 bits behind)
+        if (lane == 0 && t >= V2_RING) { spin_until_ge(&sh.peer_progress, (u32)(t + 1 - V2_RING)); spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING)); }
         __syncwarp();
-        if (lane < MIX_PER_CTA) sh1->ring_in[r][lane] = cmine;
-        // to the T warp
-        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING)); }
-        __syncwarp();
-        if (lane < MIX_PER_CTA) sh.ring_t[r][lane] = cmine;
+        if (lane < MIX_PER_CTA) { ll_store(&sh1->ring_in[r][lane], cmine, (u32)(t + 1)); ll_store(&sh.ring_t[r][lane], cmine, (u32)(t + 1)); }
         else if (lane < MIX_PER_CTA + 3) {
           const int idx = lane == MIX_PER_CTA ? 433 : (lane == MIX_PER_CTA + 1 ? 2024 : 2077);
-          sh.ring_t[r][N_L0 + (lane - MIX_PER_CTA)] = clamp_stretched(T, x[idx]);
+          ll_store(&sh.ring_t[r][N_L0 + (lane - MIX_PER_CTA)], clamp_stretched(T, x[idx]), (u32)(t + 1));
         }
-        __syncwarp();
-        fence_cluster();
-        if (lane == 0) { sh1->ring_in_seq[r] = (u32)(t + 1); sh.ring_t_seq_a[r] = (u32)(t + 1); }
       } else {
-        if (lane == 0) { if (t >= V2_RING) spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING)); }
+        if (lane == 0 && t >= V2_RING) spin_until_ge(&sh.t_consumed, (u32)(t + 1 - V2_RING));
         __syncwarp();
-        if (lane < MIX_PER_CTA) sh0->ring_t[r][MIX_PER_CTA + lane] = cmine;
-        __syncwarp();
-        fence_cluster();
-        if (lane == 0) sh0->ring_t_seq_b[r] = (u32)(t + 1);
+        if (lane < MIX_PER_CTA) ll_store(&sh0->ring_t[r][MIX_PER_CTA + lane], cmine, (u32)(t + 1));
       }
       V2_PROF(pc_on, pb + 5);
       named_arrive(BAR_COEFF, V2_CM_THREADS);
     }
-  } else if (warp < V2_T_WARP && (warp & 3) != 3) {
+    V2_PROF_DUMP(pc_on, pb, 6);
+  } else if (warp < V2_T_WARP && (warp & 3) < 2) {
     // =============================== M warps ===============================
-    const int mtid = (warp - (warp >> 2)) * 32 + lane;
+    const int mtid = ((warp >> 2) * 2 + (warp & 3)) * 32 + lane;
     const bool pm_on = a.prof != nullptr && mtid == 0 && rank == 0;
+    unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
     for (u64 t = 0; t <= n_bits; ++t) {
       // ---- prep bit t: inputs, selectors, rows ----
@@ -313,6 +369,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         }
         if (mtid == 0) {
           int nj = 0;
+#pragma unroll 1
           for (int i = 0; i < MIX_PER_CTA; ++i) {
             const u32 s = sh.want[i];
             const int cur = sh.buf_cur[i], alt = sh.buf_alt[i];
@@ -340,18 +397,34 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         V2_PROF(pm_on, 22);
         named_sync(BAR_COEFF, V2_CM_THREADS);
         V2_PROF(pm_on, 23);
-        const float* xp = sh.x[parp];
+        const float4* xp4 = reinterpret_cast<const float4*>(sh.x[parp]);
         const float* ex = sh.extras[parp];
-        for (int i = 0; i < MIX_PER_CTA; ++i) {
+        // w -= update * x over 13 rows x 2078 inputs, float4 at a time (mixer.cpp:66-71)
+#pragma unroll 2
+        for (int idx = mtid; idx < MIX_PER_CTA * 520; idx += V2_M_THREADS) {
+          const int i = idx / 520, k4 = idx - i * 520;
           const float u = sh.upd[i];
           const bool shr = sh.shrink[i] != 0;
-          float* row = sh.rows[sh.buf_cur[i]];
-          const int n = N_INPUTS + m0 + i;
-          for (int k = mtid; k < n; k += V2_M_THREADS) {
-            const float xin = k < N_INPUTS ? xp[k] : ex[k - N_INPUTS];
-            float w = XM_FSUB(row[k], XM_FMUL(u, xin));
-            if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
-            row[k] = w;
+          float4* row4 = reinterpret_cast<float4*>(sh.rows[sh.buf_cur[i]]);
+          if (k4 < 519) {
+            const float4 xv = xp4[k4];
+            float4 w = row4[k4];
+            w.x = XM_FSUB(w.x, XM_FMUL(u, xv.x)); w.y = XM_FSUB(w.y, XM_FMUL(u, xv.y));
+            w.z = XM_FSUB(w.z, XM_FMUL(u, xv.z)); w.w = XM_FSUB(w.w, XM_FMUL(u, xv.w));
+            if (shr) { w.x = XM_FMUL(w.x, 1.0f - 3.0e-6f); w.y = XM_FMUL(w.y, 1.0f - 3.0e-6f); w.z = XM_FMUL(w.z, 1.0f - 3.0e-6f); w.w = XM_FMUL(w.w, 1.0f - 3.0e-6f); }
+            row4[k4] = w;
+          } else {
+            // tail: inputs 2076, 2077 and this mixer's extra inputs (2078 .. 2078 + m0 + i - 1)
+            float* row = sh.rows[sh.buf_cur[i]];
+            const float* xs = sh.x[parp];
+            const int n = N_INPUTS + m0 + i;
+#pragma unroll 1
+            for (int k = 2076; k < n; ++k) {
+              const float xin = k < N_INPUTS ? xs[k] : ex[k - N_INPUTS];
+              float w = XM_FSUB(row[k], XM_FMUL(u, xin));
+              if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+              row[k] = w;
+            }
           }
         }
         if (mtid < MIX_PER_CTA) sh.dirty[sh.buf_cur[mtid]] = 1;
@@ -362,6 +435,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         // ---- make the rows of bit t current: swap prefetched buffers, late-switch single-buffer rows ----
         if (mtid == 0) {
           int nj = 0;
+#pragma unroll 1
           for (int i = 0; i < MIX_PER_CTA; ++i) {
             if (sh.swap_needed[i]) { const int c = sh.buf_cur[i]; sh.buf_cur[i] = sh.buf_alt[i]; sh.buf_alt[i] = c; }
             else if (sh.late[i]) {
@@ -374,15 +448,18 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
           sh.n_jobs = nj;
         }
         named_sync(BAR_MOVERS, V2_M_THREADS);
-        if (sh.n_jobs) run_row_jobs(sh, st, m0, mtid);
+        run_row_jobs(sh, st, m0, mtid);
         V2_PROF(pm_on, 25);
         named_arrive(BAR_READY, V2_CM_THREADS);
       }
     }
+    V2_PROF_DUMP(pm_on, 20, 6);
     // ---- epilogue: write every dirty resident row back ----
     if (mtid == 0) {
       int nj = 0;
+#pragma unroll 1
       for (int i = 0; i < MIX_PER_CTA; ++i) {
+#pragma unroll 1
         for (int w = 0; w < 2; ++w) {
           const int b = w == 0 ? sh.buf_cur[i] : sh.buf_alt[i];
           if (b < 0 || sh.tag[b] == 0xffffffffu || !sh.dirty[b]) continue;
@@ -395,6 +472,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
     }
     named_sync(BAR_MOVERS, V2_M_THREADS);
     run_row_jobs(sh, st, m0, mtid);
+    if (mtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // evictions complete before the kernel ends
   } else if (rank == 0 && warp == V2_T_WARP) {
     // =============================== T warp (CTA 0, warp 14) ===============================
     // Layers 1/2 + SSE, one bit behind the layer-0 recurrence. All HBM-latency-bound lookups
@@ -408,6 +486,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
     const float mylr = mym.lr;
     u64 my_max = mym.max_steps; u32 my_assigned = mym.n_assigned; const u32 my_nrows = mym.n_rows;
     const bool pt_on = a.prof != nullptr && lane == 0;
+    unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
     u32 myslot = 0xffffffffu; u64 my_rs = 0;
     for (u64 t = 0; t < n_bits; ++t) {
@@ -459,22 +538,24 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
       __syncwarp();
       V2_PROF(pt_on, 26);
       // ---- wait for the 26 clamped layer-0 outputs + 3 auxiliary inputs of bit t ----
-      if (lane == 0) { spin_until_ge(&sh.ring_t_seq_a[r], (u32)(t + 1)); spin_until_ge(&sh.ring_t_seq_b[r], (u32)(t + 1)); }
+      {
+        float c = 0.0f;
+        if (lane < N_L0 + N_AUX) c = ll_wait(&sh.ring_t[r][lane], (u32)(t + 1));
+        if (lane < N_L0) { sh.in1[lane] = c; sh.in2[lane] = c; }
+        else if (lane < N_L0 + N_AUX) { sh.in1[lane] = c; sh.in2[N_L1 + lane] = c; }
+      }
       __syncwarp();
       V2_PROF(pt_on, 27);
-      fence_cluster();
-      if (lane < N_L0) { const float c = sh.ring_t[r][lane]; sh.in1[lane] = c; sh.in2[lane] = c; }
-      if (lane < N_AUX) { const float c = sh.ring_t[r][N_L0 + lane]; sh.in1[N_L0 + lane] = c; sh.in2[N_L0 + N_L1 + lane] = c; }
-      __syncwarp();
-      if (lane == 0) { fence_cluster(); sh.t_consumed = (u32)(t + 1); sh1->t_consumed = (u32)(t + 1); }
+      if (lane == 0) { sh.t_consumed = (u32)(t + 1); sh1->t_consumed = (u32)(t + 1); }
       // ---- layer 1 ----
       float main = 0.0f;
       if (lane < N_L1) {
         const float* w = sh.l1row[lane];
-#pragma unroll
+#pragma unroll 4
         for (int k = 0; k < L1_IN; ++k) main = XM_FADD(main, XM_FMUL(sh.in1[k], w[k]));
       }
       float e = 0.0f, pfin = 0.0f;
+#pragma unroll 1
       for (int k = 0; k < N_L1; ++k) {
         if (lane == k) pfin = XM_FADD(main, e);
         const float pk = __shfl_sync(0xffffffffu, pfin, k);
@@ -483,10 +564,11 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         if (lane > k && lane < N_L1) e = XM_FADD(e, XM_FMUL(ck, sh.l1row[lane][L1_IN + k]));
       }
       __syncwarp();
+      V2_PROF(pt_on, 28);
       // ---- layer 2 (lane 20 owns the mixer; computed by all lanes redundantly is not needed) ----
       float s2 = 0.0f;
       if (lane == N_L1) {
-#pragma unroll
+#pragma unroll 7
         for (int k = 0; k < L2_IN; ++k) s2 = XM_FADD(s2, XM_FMUL(sh.in2[k], sh.l2row[k]));
         s2 = XM_FADD(s2, 0.0f);
         pfin = s2;
@@ -535,30 +617,38 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         u16* g7 = sse.s7 + i7 * 8; g7[qq7] = k7[qq7]; g7[qq7 + 1] = k7[qq7 + 1];
         sse.x1[ix1] = wx1; sse.x2[ix2] = wx2;
       }
+      V2_PROF(pt_on, 29);
       sj += sj + bit;
       if (sj >= 256) { sffl = (u8)(sffl * 2 + (spc >= 0x40)); spc = (u8)sj; sj = 1; }
       // ---- SGD of layers 1/2 (mixer.cpp:56-72) on the lane-owned resident rows ----
       const float decay = a.decay[t];
+      float u_mine = 0.0f; u32 shr_mine = 0;
       if (lane < N_L1 + 1) {
         float d = decay;
         d = (float)((double)d * (1.5 - ((1.0 * (double)my_rs) / (double)my_max)));
         const float u = XM_FMUL(XM_FMUL(d, mylr), XM_FSUB(xm_logistic(pfin), (float)bit));
         my_rs += 1;
         if (my_rs > my_max) my_max = my_rs;
-        const bool shr = (my_rs & 1023) == 0;
-        float* row = lane < N_L1 ? sh.l1row[lane] : sh.l2row;
-        const int n = lane < N_L1 ? L1_IN + lane : L2_IN;
-        for (int c = 0; c < n; ++c) {
-          const float xin = lane < N_L1 ? (c < L1_IN ? sh.in1[c] : sh.l1extra[c - L1_IN]) : sh.in2[c];
-          float w = XM_FSUB(row[c], XM_FMUL(u, xin));
-          if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+        shr_mine = (my_rs & 1023) == 0 ? 1u : 0u;
+        u_mine = u;
+      }
+#pragma unroll 1
+      for (int i = 0; i < N_L1 + 1; ++i) {                 // row i: lanes sweep its columns (independent elements)
+        const float ui = __shfl_sync(0xffffffffu, u_mine, i);
+        const u32 shi = __shfl_sync(0xffffffffu, shr_mine, i);
+        float* row = i < N_L1 ? sh.l1row[i] : sh.l2row;
+        const int n = i < N_L1 ? L1_IN + i : L2_IN;
+        for (int c = lane; c < n; c += 32) {
+          const float xin = i < N_L1 ? (c < L1_IN ? sh.in1[c] : sh.l1extra[c - L1_IN]) : sh.in2[c];
+          float w = XM_FSUB(row[c], XM_FMUL(ui, xin));
+          if (shi) w = XM_FMUL(w, 1.0f - 3.0e-6f);
           row[c] = w;
         }
       }
       __syncwarp();
-      __threadfence_block();
-      V2_PROF(pt_on, 28);
+      V2_PROF(pt_on, 30);
     }
+    V2_PROF_DUMP(pt_on, 26, 5);
     if (lane < N_L1 + 1) {
       if (myslot != 0xffffffffu) {
         const float* srow = lane < N_L1 ? sh.l1row[lane] : sh.l2row;

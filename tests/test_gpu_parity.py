@@ -172,3 +172,20 @@ def test_fresh_reference_dump_on_this_box(cm, tmp_path):
     ideal = -np.log2(np.where(bits == 1, p, 1 - p).clip(1e-9, 1)).sum() / 8 / d.n_bytes * 8
     ideal_ref = -np.log2(np.where(bits == 1, d.p, 1 - d.p).clip(1e-9, 1)).sum() / 8 / d.n_bytes * 8
     assert abs(ideal - ideal_ref) <= 0.001          # bits per byte within 0.001 of the reference
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "build", "cmix_b200_cli")),
+                    reason="reference CLI + shim not built (make -C cmix_b200/shim)")
+def test_reference_cli_round_trip(tmp_path):
+    """The reference's own runner + arithmetic coder, compiled unchanged against the shim
+    (INTEGRATION.md): compress then decompress through Predict()/Perceive() on the GPU."""
+    from gen_synth import synth_text
+    cli = os.path.join(ROOT, "build", "cmix_b200_cli")
+    src = tmp_path / "in.txt"
+    data = synth_text(700, 0xE9E80005)
+    src.write_bytes(data)
+    arc, back = tmp_path / "out.cmix", tmp_path / "back.txt"
+    subprocess.run([cli, "-c", str(src), str(arc)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    subprocess.run([cli, "-d", str(arc), str(back)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    assert back.read_bytes() == data
+    assert arc.stat().st_size < len(data)
