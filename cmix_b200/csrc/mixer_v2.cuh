@@ -206,13 +206,14 @@ __device__ __forceinline__ void run_row_jobs(MixShared2& sh, StreamState* st, in
 }
 
 // Stage the 2078 layer-0 inputs with all global loads issued before any use (2 round trips).
+template <int NT>
 __device__ __forceinline__ void stage_inputs_v2(float* x, const float* lut, const u16* ext, const float* small_x,
                                                 float lstm_x, int mtid) {
-  enum { PER = (N_INPUTS + V2_M_THREADS - 1) / V2_M_THREADS };   // 6
+  enum { PER = (N_INPUTS + NT - 1) / NT };
   u32 code[PER]; float direct[PER];
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
-    const int k = mtid + q * V2_M_THREADS;
+    const int k = mtid + q * NT;
     code[q] = 0x10000u; direct[q] = 0.0f;
     if (k < N_INPUTS) {
       if (k < 3) direct[q] = small_x[k];
@@ -224,7 +225,7 @@ __device__ __forceinline__ void stage_inputs_v2(float* x, const float* lut, cons
   }
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
-    const int k = mtid + q * V2_M_THREADS;
+    const int k = mtid + q * NT;
     if (k < N_INPUTS) x[k] = code[q] == 0x10000u ? direct[q] : lut[code[q] == 0xFFFFu ? 4096 : code[q]];
   }
 }
@@ -359,7 +360,7 @@ mix_kernel_v2(const ChunkArgs* __restrict__ args_all, Tables T) {
         if (mtid < SEL_PITCH) sh.sel[par][mtid] = mtid < N_MIXERS ? a.sel[t * SEL_PITCH + mtid] : 0;
         if (mtid >= 64 && mtid < 64 + MIX_PER_CTA && !(rank == 0 && mtid - 64 == 12))
           sh.want[mtid - 64] = resolve_slot(st->mixer[m0 + mtid - 64], a.sel[t * SEL_PITCH + m0 + mtid - 64]);
-        stage_inputs_v2(sh.x[par], sh.lut12, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], mtid);
+        stage_inputs_v2<V2_M_THREADS>(sh.x[par], sh.lut12, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], mtid);
         named_sync(BAR_MOVERS, V2_M_THREADS);
         V2_PROF(pm_on, 20);
         if (rank == 0 && mtid == 0) {

@@ -26,7 +26,7 @@
 
 namespace cmixb200 {
 
-enum { V3_NBUF = 20, V3_RING = 4, V3_M_THREADS = 256, V3_CM = V3_M_THREADS + 32,
+enum { V3_NBUF = 20, V3_RING = 4, V3_M_WARPS = 11, V3_M_THREADS = V3_M_WARPS * 32, V3_CM = V3_M_THREADS + 32,
        B3_READY0 = 1, B3_COEFF0 = 3, B3_MOVERS = 5,
        K_SAME = 0, K_SWAP = 1, K_LATE_SAME = 2, K_LATE_SWITCH = 3, T_ELEMS = 819 };
 
@@ -104,25 +104,31 @@ __device__ __forceinline__ float chain_fused(const float* __restrict__ x, float*
   return p;
 }
 
-enum { V3_CHUNKS = 8, V3_CHUNK4 = 65 };          // 8 chunks of 65 float4 (the last: 64 + the scalar tail)
+enum { V3_CHUNKS = 8, V3_CHUNK4 = 64 };          // 8 chunks of 64 float4; the last also takes float4 512..518 and the scalar tail
 
-// One chunk of the serial dot product (plain, the SGD step is applied by the movers chunk by chunk
-// just ahead of this warp). Double-buffered loads, 4 float4 per block.
+// One chunk (64 float4) of the serial dot product; the SGD step is applied by the movers chunk by
+// chunk just ahead of this warp. Ping-pong register buffers keep 8 LDS.128 in flight under the FADD chain.
 __device__ __forceinline__ float chain_chunk(const float4* __restrict__ x4, const float4* __restrict__ w4, int k0, int k1, float p) {
-  int k = k0;
+  float4 xa[4], wa[4], xb[4], wb[4];
+#define CC_LOAD(X, W, k) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { X[q] = x4[(k) + q]; W[q] = w4[(k) + q]; } }
+#define CC_EAT(X, W) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
+    p = XM_FADD(p, XM_FMUL(X[q].x, W[q].x)); p = XM_FADD(p, XM_FMUL(X[q].y, W[q].y)); \
+    p = XM_FADD(p, XM_FMUL(X[q].z, W[q].z)); p = XM_FADD(p, XM_FMUL(X[q].w, W[q].w)); } }
+  CC_LOAD(xa, wa, k0);
 #pragma unroll 1
-  for (; k + 4 <= k1; k += 4) {
-    float4 xa[4], wa[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { xa[q] = x4[k + q]; wa[q] = w4[k + q]; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      p = XM_FADD(p, XM_FMUL(xa[q].x, wa[q].x)); p = XM_FADD(p, XM_FMUL(xa[q].y, wa[q].y));
-      p = XM_FADD(p, XM_FMUL(xa[q].z, wa[q].z)); p = XM_FADD(p, XM_FMUL(xa[q].w, wa[q].w));
-    }
+  for (int k = k0; k < k0 + 56; k += 8) {          // blocks 0..13 consumed, block 14 left in A
+    CC_LOAD(xb, wb, k + 4);
+    CC_EAT(xa, wa);
+    CC_LOAD(xa, wa, k + 8);
+    CC_EAT(xb, wb);
   }
+  CC_LOAD(xb, wb, k0 + 60);
+  CC_EAT(xa, wa);
+  CC_EAT(xb, wb);
+#undef CC_LOAD
+#undef CC_EAT
 #pragma unroll 1
-  for (; k < k1; ++k) {
+  for (int k = k0 + 64; k < k1; ++k) {              // only the last chunk: float4 512..518
     const float4 a = x4[k], b = w4[k];
     p = XM_FADD(p, XM_FMUL(a.x, b.x)); p = XM_FADD(p, XM_FMUL(a.y, b.y));
     p = XM_FADD(p, XM_FMUL(a.z, b.z)); p = XM_FADD(p, XM_FMUL(a.w, b.w));
@@ -130,36 +136,47 @@ __device__ __forceinline__ float chain_chunk(const float4* __restrict__ x4, cons
   return p;
 }
 
-// movers: apply the SGD step of one bit, chunk c only, to the rows listed in sh.mupd (-1 = none)
-__device__ __forceinline__ void movers_update_chunk(MixShared3& sh, int m0, int mtid, int par_prev, const float* xprev, int c) {
+// movers: apply the SGD step of one bit, chunk c only, to the rows listed in sh.mupd (-1 = none).
+// Work item = (row, half chunk of 32 float4): one warp instruction stream per item, no index division.
+__device__ __forceinline__ void movers_update_chunk(MixShared3& sh, int m0, int mwarp, int lane, int par_prev, const float* xprev, int c) {
   const float4* xp4 = reinterpret_cast<const float4*>(xprev);
-  const float* ex = sh.cext[par_prev];
-  const int k0 = c * V3_CHUNK4;
-  const int per = V3_CHUNK4 + (c == V3_CHUNKS - 1 ? 0 : 0);
-#pragma unroll 2
-  for (int idx = mtid; idx < MIX_PER_CTA * per; idx += V3_M_THREADS) {
-    const int i = idx / per, k4 = k0 + (idx - i * per);
+#pragma unroll 1
+  for (int item = mwarp; item < 2 * MIX_PER_CTA; item += V3_M_WARPS) {
+    const int i = item >> 1, half = item & 1;
     const int b = sh.mupd[i];
     if (b < 0) continue;
     const float u = sh.upd[par_prev][i];
     const bool shr = sh.plan_shrink[par_prev][i] != 0;
-    if (k4 < 519) {
-      float4* row4 = reinterpret_cast<float4*>(sh.rows[b]);
+    float4* row4 = reinterpret_cast<float4*>(sh.rows[b]);
+    {
+      const int k4 = c * V3_CHUNK4 + half * 32 + lane;
       const float4 xv = xp4[k4];
       float4 w = row4[k4];
       w.x = XM_FSUB(w.x, XM_FMUL(u, xv.x)); w.y = XM_FSUB(w.y, XM_FMUL(u, xv.y));
       w.z = XM_FSUB(w.z, XM_FMUL(u, xv.z)); w.w = XM_FSUB(w.w, XM_FMUL(u, xv.w));
       if (shr) { w.x = XM_FMUL(w.x, 1.0f - 3.0e-6f); w.y = XM_FMUL(w.y, 1.0f - 3.0e-6f); w.z = XM_FMUL(w.z, 1.0f - 3.0e-6f); w.w = XM_FMUL(w.w, 1.0f - 3.0e-6f); }
       row4[k4] = w;
-    } else if (k4 == 519) {
-      float* row = sh.rows[b];
-      const int n = N_INPUTS + m0 + i;
+    }
+    if (c == V3_CHUNKS - 1 && half == 1) {
+      // leftovers of the row: float4 512..518, scalars 2076/2077 and this mixer's extra-input weights
+      if (lane < 7) {
+        const int k4 = 512 + lane;
+        const float4 xv = xp4[k4];
+        float4 w = row4[k4];
+        w.x = XM_FSUB(w.x, XM_FMUL(u, xv.x)); w.y = XM_FSUB(w.y, XM_FMUL(u, xv.y));
+        w.z = XM_FSUB(w.z, XM_FMUL(u, xv.z)); w.w = XM_FSUB(w.w, XM_FMUL(u, xv.w));
+        if (shr) { w.x = XM_FMUL(w.x, 1.0f - 3.0e-6f); w.y = XM_FMUL(w.y, 1.0f - 3.0e-6f); w.z = XM_FMUL(w.z, 1.0f - 3.0e-6f); w.w = XM_FMUL(w.w, 1.0f - 3.0e-6f); }
+        row4[k4] = w;
+      } else {
+        const int n = N_INPUTS + m0 + i;
+        float* row = sh.rows[b];
 #pragma unroll 1
-      for (int k = 2076; k < n; ++k) {
-        const float xin = k < N_INPUTS ? xprev[k] : ex[k - N_INPUTS];
-        float w = XM_FSUB(row[k], XM_FMUL(u, xin));
-        if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
-        row[k] = w;
+        for (int k = 2076 + (lane - 7); k < n; k += 25) {   // lanes 7..31 sweep elements 2076 .. n-1
+          const float xin = k < N_INPUTS ? xprev[k] : sh.cext[par_prev][k - N_INPUTS];
+          float w = XM_FSUB(row[k], XM_FMUL(u, xin));
+          if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+          row[k] = w;
+        }
       }
     }
   }
@@ -168,7 +185,7 @@ __device__ __forceinline__ void movers_update_chunk(MixShared3& sh, int m0, int 
 __device__ __forceinline__ void movers_update(MixShared3& sh, int m0, int mtid, int par_prev, const float* xprev, u32 seq) {
 #pragma unroll 1
   for (int c = 0; c < V3_CHUNKS; ++c) {
-    movers_update_chunk(sh, m0, mtid, par_prev, xprev, c);
+    movers_update_chunk(sh, m0, mtid >> 5, mtid & 31, par_prev, xprev, c);
     named_sync(B3_MOVERS, V3_M_THREADS);
     if (mtid == 0) sh.chunk_seq[c] = seq;
   }
@@ -298,7 +315,7 @@ mix_kernel_v3(const ChunkArgs* __restrict__ args_all, Tables T) {
 #pragma unroll 1
         for (int c = 0; c < V3_CHUNKS; ++c) {
           while (sh.chunk_seq[c] < (u32)t) { }            // the movers have applied bit t-1's step to this chunk
-          if (lane < MIX_PER_CTA) main = chain_chunk(x4, w4, c * V3_CHUNK4, min(519, (c + 1) * V3_CHUNK4), main);
+          if (lane < MIX_PER_CTA) main = chain_chunk(x4, w4, c * V3_CHUNK4, c == V3_CHUNKS - 1 ? 519 : (c + 1) * V3_CHUNK4, main);
         }
         if (lane < MIX_PER_CTA) {
           main = XM_FADD(main, XM_FMUL(x[2076], row[2076]));
@@ -357,9 +374,9 @@ mix_kernel_v3(const ChunkArgs* __restrict__ args_all, Tables T) {
       V3_PROF(pc_on, pb + 5);
     }
     V2_PROF_DUMP(pc_on, pb, 6);
-  } else if (warp < V2_T_WARP && (warp & 3) < 2) {
+  } else if (warp < V2_T_WARP && (warp & 3) != 3) {
     // =============================== M warps ===============================
-    const int mtid = ((warp >> 2) * 2 + (warp & 3)) * 32 + lane;
+    const int mtid = (warp - (warp >> 2)) * 32 + lane;
     const bool pm_on = a.prof != nullptr && mtid == 0 && rank == 0;
     unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
@@ -372,7 +389,7 @@ mix_kernel_v3(const ChunkArgs* __restrict__ args_all, Tables T) {
         if (mtid < SEL_PITCH) sh.sel[par][mtid] = mtid < N_MIXERS ? a.sel[t * SEL_PITCH + mtid] : 0;
         if (mtid >= 64 && mtid < 64 + MIX_PER_CTA && !(rank == 0 && mtid - 64 == 12))
           sh.want[mtid - 64] = resolve_slot(st->mixer[m0 + mtid - 64], a.sel[t * SEL_PITCH + m0 + mtid - 64]);
-        stage_inputs_v2(sh.x[t % 3], sh.lut12, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], mtid);
+        stage_inputs_v2<V3_M_THREADS>(sh.x[t % 3], sh.lut12, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], mtid);
         named_sync(B3_MOVERS, V3_M_THREADS);
         V3_PROF(pm_on, 20);
         if (mtid == 0) {
