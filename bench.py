@@ -179,6 +179,7 @@ def main():
     import torch
     import cmix_b200
     from cmix_b200.capi import code_batch_device
+    from cmix_b200.sharding import stream_block, reduce_timing
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
     dist = None
@@ -192,8 +193,8 @@ def main():
     total_steps = K + W
     # ---- inputs resident in HBM before the timed region ----
     streams = []
-    for s in range(S):
-        text, vocab, d_bytes, d_ext, d_ppmd = make_inputs(torch, dev, B * total_steps, seed=rank * 1000 + s)
+    for s in stream_block(S * world, world, rank):      # global stream ids owned by this rank (weak scaling: S per GPU)
+        text, vocab, d_bytes, d_ext, d_ppmd = make_inputs(torch, dev, B * total_steps, seed=s)
         P = cmix_b200.Predictor(vocab, device=local_rank)
         d_out = torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)
         streams.append(dict(P=P, text=text, d_bytes=d_bytes, d_ext=d_ext, d_ppmd=d_ppmd, d_out=d_out))
@@ -226,15 +227,13 @@ def main():
     dt = max(time.perf_counter() - t0, ev0.elapsed_time(ev1) / 1e3)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    bytes_per_rank = S * B * K
+    total_bytes = bytes_per_rank * world
     if dist:
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt, total_bytes = reduce_timing(dist, dev, dt, bytes_per_rank)
         dist.barrier()
     launches = sum(st["P"].kernel_launches for st in streams) - launches0
     mix_ms, mix_n = streams[0]["P"].mix_kernel_ms()
-    bytes_per_rank = S * B * K
-    total_bytes = bytes_per_rank * world
     value = total_bytes / dt / 1e6
 
     # ---- end to end through the C-ABI with host buffers (pinned), stream 0 of this rank ----
