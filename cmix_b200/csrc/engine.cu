@@ -239,6 +239,7 @@ int BuildSharedTables(int device) {
   CK(cudaMemcpyToSymbol(c_runmap, runmap, sizeof runmap));
   CK(cudaMemcpyToSymbol(c_ivmap, ivmap, sizeof ivmap));
   CK(cudaMemcpyToSymbol(c_mixer_sel, msel, sizeof msel));
+  CK(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallState)));
   CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(mix_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared2)));
   CK(cudaFuncSetAttribute(mix_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared3)));
@@ -415,25 +416,26 @@ int BuildStream(cmixb200_predictor* P) {
       for (int e = 0; e < H; ++e) inp[(size_t)e * Y.in_size + Y.in_size - 1] = 1;
       TRY(P->Alloc(&Y.input, inp.size(), false));
       CK(cudaMemcpy(Y.input, inp.data(), inp.size() * 4, cudaMemcpyHostToDevice));
+      const size_t wsize = (size_t)lstm_rowp(V, Y.in_size) * C;
       std::vector<float> w[3];
-      for (int g = 0; g < 3; ++g) w[g].assign((size_t)row * C, 0.0f);
+      for (int g = 0; g < 3; ++g) w[g].assign(wsize, 0.0f);
       const float val = sqrt(6.0f / float(V + V));
       const float low = -val, range = 2 * val;
       auto rnd = [&]() { return static_cast<float>(rng.next()) / static_cast<float>(RAND_MAX); };
       for (int i = 0; i < C; ++i) {
         for (int j = 0; j < row; ++j) {
-          w[0][lstm_widx(row, j, i)] = low + rnd() * range;
-          w[1][lstm_widx(row, j, i)] = low + rnd() * range;
-          w[2][lstm_widx(row, j, i)] = low + rnd() * range;
+          w[0][lstm_widx(V, Y.in_size, j, i)] = low + rnd() * range;
+          w[1][lstm_widx(V, Y.in_size, j, i)] = low + rnd() * range;
+          w[2][lstm_widx(V, Y.in_size, j, i)] = low + rnd() * range;
         }
-        w[0][lstm_widx(row, row - 1, i)] = 1;
+        w[0][lstm_widx(V, Y.in_size, row - 1, i)] = 1;
       }
       for (int g = 0; g < 3; ++g) {
         GateState& G = Y.gate[g];
         G.row = row;
-        TRY(P->Alloc(&G.w, (size_t)row * C, false));
+        TRY(P->Alloc(&G.w, wsize, false));
         CK(cudaMemcpy(G.w, w[g].data(), w[g].size() * 4, cudaMemcpyHostToDevice));
-        TRY(P->Alloc(&G.m, (size_t)row * C)); TRY(P->Alloc(&G.v, (size_t)row * C));
+        TRY(P->Alloc(&G.m, wsize)); TRY(P->Alloc(&G.v, wsize));
         TRY(P->Alloc(&G.state, H * C)); TRY(P->Alloc(&G.norm, H * C)); TRY(P->Alloc(&G.err, H * C));
         for (int i = 0; i < C; ++i) G.gamma[i] = 1.0f;
       }
@@ -481,7 +483,7 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 // Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain) {
   const Tables T = g_tables.T;
-  small_kernel<<<n_streams, 64, 0, lead->s_small>>>(d_args, T);
+  small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
   lead->launches++;
   if (!pretrain) {
     lstm_kernel<<<LSTM_CTAS * n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);

@@ -39,8 +39,14 @@ enum { LSTM_THREADS = 512, LSTM_CTAS = 8, LCPC = 25 /* cells per CTA */, LSTM_PO
 #define LC LSTM_CELLS
 #define LH LSTM_HORIZON
 
-__host__ __device__ __forceinline__ size_t lstm_widx(int row, int col, int cell) {
-  return ((size_t)(cell / LCPC) * row + col) * LCPC + (cell % LCPC);
+// Weight layout (per gate): [8 cell blocks][padded column][25 cells]. Columns: the V one-hot columns,
+// padded to a multiple of 4, then the dense columns (input vector), padded to a multiple of 4 - so the
+// dense slice of a cell block starts on a 16-byte boundary and is a whole number of 16-byte units.
+__host__ __device__ __forceinline__ int lstm_vp(int V) { return (V + 3) & ~3; }
+__host__ __device__ __forceinline__ int lstm_rowp(int V, int in_size) { return lstm_vp(V) + ((in_size + 3) & ~3); }
+__host__ __device__ __forceinline__ size_t lstm_widx(int V, int in_size, int col, int cell) {
+  const int pc = col < V ? col : lstm_vp(V) + (col - V);
+  return ((size_t)(cell / LCPC) * lstm_rowp(V, in_size) + pc) * LCPC + (cell % LCPC);
 }
 
 struct LstmShared {
@@ -57,6 +63,13 @@ struct LstmShared {
   int sym[LH];
   alignas(16) float pool[LSTM_POOL_FLOATS];
 };
+
+#define L_PROF(slot) do { if (prof) { unsigned d_ = *reinterpret_cast<volatile unsigned*>(&sh.sym[0]), k_; \
+    asm volatile("mov.u32 %0, %1;" : "=r"(k_) : "r"(d_)); const long long n_ = clock64(); prof[slot] += (unsigned long long)(n_ - *tprev) + (k_ & 0u); *tprev = n_; } } while (0)
+
+__device__ __noinline__ float lt_tanhf(float x) { return xm_tanhf(x); }
+__device__ __noinline__ float lt_logistic(float x) { return xm_logistic(x); }
+__device__ __noinline__ float lt_expf(float x) { return xm_expf(x); }
 
 __device__ __forceinline__ float clipf(float v, float c) { return v < -c ? -c : (v > c ? c : v); }
 
@@ -77,7 +90,7 @@ __device__ __forceinline__ void lcp_async_wait() {
 __device__ __forceinline__ void gather75(cgl::cluster_group& cluster, float (*dst)[LC], int rank, int tid, float v) {
   if (tid < 3 * LCPC) {
     const int g = tid / LCPC, i = tid % LCPC;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(dst, c);
       rd[g][LCPC * rank + i] = v;
@@ -86,50 +99,47 @@ __device__ __forceinline__ void gather75(cgl::cluster_group& cluster, float (*ds
 }
 
 // LstmLayer::ForwardPass (lstm-layer.cpp:62-99) for one layer; the whole cluster.
-__device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, int l, int sym, LstmShared& sh, int rank, int tid) {
+__device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, int l, int sym, LstmShared& sh, int rank, int tid,
+                                   unsigned long long* prof, long long* tprev) {
   LayerState& L = S.layer[l];
-  const int V = S.V, e = L.epoch, in_size = L.in_size, row = in_size + V;
+  const int V = S.V, e = L.epoch, in_size = L.in_size;
   const float* in_g = L.input + (size_t)e * in_size;
   // ---- stage: input vector + this CTA's weight slice (dense columns, then the symbol column) ----
   for (int j = tid; j < in_size; j += LSTM_THREADS) sh.in[j] = in_g[j];
-  const int n4 = in_size * LCPC / 4;           // floats per gate slice, dense part (in_size*25 is a multiple of 4? see below)
+  const int in_sizep = (in_size + 3) & ~3, rowp = lstm_rowp(V, in_size), gstride = (in_sizep + 4) * LCPC;
   for (int g = 0; g < 3; ++g) {
-    const float* src = L.gate[g].w + ((size_t)rank * row + V) * LCPC;     // [col >= V][25]
-    float* dst = sh.pool + (size_t)g * (in_size + 1) * LCPC;
-    const int nflt = in_size * LCPC;
-    // 16-byte copies where both sides are aligned; tail / unaligned with 4-byte copies
-    const bool al = ((((size_t)src) | ((size_t)dst)) & 15) == 0;
-    if (al) {
-      for (int k = tid; k < nflt / 4; k += LSTM_THREADS) lcp_async16(dst + 4 * k, src + 4 * k);
-      for (int k = (nflt / 4) * 4 + tid; k < nflt; k += LSTM_THREADS) lcp_async4(dst + k, src + k);
-    } else {
-      for (int k = tid; k < nflt; k += LSTM_THREADS) lcp_async4(dst + k, src + k);
-    }
-    const float* ssrc = L.gate[g].w + ((size_t)rank * row + sym) * LCPC;   // column `sym`
-    if (tid < LCPC) lcp_async4(dst + nflt + tid, ssrc + tid);
+    const float* src = L.gate[g].w + ((size_t)rank * rowp + lstm_vp(V)) * LCPC;     // dense columns, 16-byte aligned
+    float* dst = sh.pool + (size_t)g * gstride;
+    const int n16 = in_sizep * LCPC / 4;
+    for (int k = tid; k < n16; k += LSTM_THREADS) lcp_async16(dst + 4 * k, src + 4 * k);
+    const float* ssrc = L.gate[g].w + ((size_t)rank * rowp + sym) * LCPC;           // one-hot column `sym`
+    if (tid < LCPC) lcp_async4(dst + in_sizep * LCPC + tid, ssrc + tid);
   }
-  (void)n4;
   lcp_async_wait();
   __syncthreads();
+  L_PROF(4);
   // ---- 75 serial chains out of shared memory ----
   float f = 0.0f;
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31;
-    const float* w = sh.pool + (size_t)g * (in_size + 1) * LCPC + i;
-    f = w[(size_t)in_size * LCPC];
+    const float* w = sh.pool + (size_t)g * gstride + i;
+    f = w[(size_t)in_sizep * LCPC];
 #pragma unroll 8
     for (int j = 0; j < in_size; ++j) f = XM_FADD(f, XM_FMUL(sh.in[j], w[(size_t)j * LCPC]));
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(sh.gat, c);
       rd[g][LCPC * rank + i] = f;
     }
   }
+  L_PROF(5);
   cluster.sync();
+  L_PROF(7);
   // ---- RMS norm: every CTA computes the three sums redundantly (back to front, _Expr::sum()) ----
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
     float ss = XM_FMUL(sh.gat[g][LC - 1], sh.gat[g][LC - 1]);
+#pragma unroll 8
     for (int i = LC - 2; i >= 0; --i) ss = XM_FADD(ss, XM_FMUL(sh.gat[g][i], sh.gat[g][i]));
     const float iv = XM_FDIV(1.0f, __fsqrt_rn(XM_FADD(XM_FDIV(ss, (float)LC), 1e-5f)));
     sh.scal[g] = iv;
@@ -142,7 +152,7 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
     const float n = XM_FMUL(sh.gat[g][cell], sh.scal[g]);
     G.norm[(size_t)e * LC + cell] = n;
     float s = XM_FADD(XM_FMUL(n, G.gamma[cell]), G.beta[cell]);
-    s = (g == 1) ? xm_tanhf(s) : xm_logistic(s);
+    s = (g == 1) ? lt_tanhf(s) : lt_logistic(s);
     G.state[(size_t)e * LC + cell] = s;
     sh.act[g][i] = s;
   }
@@ -157,22 +167,25 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
     c = XM_FMUL(c, fs);
     c = XM_FADD(c, XM_FMUL(gs, ig));
     L.state[cell] = c;
-    const float ts = xm_tanhf(c);
+    const float ts = lt_tanhf(c);
     L.tanh_state[(size_t)e * LC + cell] = ts;
     const float h = XM_FMUL(os, ts);
     S.hidden[l * LC + cell] = h;
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < LSTM_CTAS; ++cc) {
       float* rh = cluster.map_shared_rank(sh.hid, cc);
       rh[l * LC + cell] = h;
     }
   }
   if (rank == 0 && tid == 0) L.epoch = (e + 1 == LH) ? 0 : e + 1;
+  L_PROF(8);
   cluster.sync();
+  L_PROF(7);
 }
 
 // Lstm::Predict (lstm.cpp:120-150)
-__device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned input, LstmShared& sh, int rank, int tid) {
+__device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned input, LstmShared& sh, int rank, int tid,
+                             unsigned long long* prof, long long* tprev) {
   const int V = S.V, e = S.epoch, HW = LSTM_HID;
   for (int l = 0; l < 2; ++l) {
     LayerState& L = S.layer[l];
@@ -184,7 +197,8 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
     }
     __threadfence();
     cluster.sync();
-    lstm_layer_forward(cluster, S, l, (int)input, sh, rank, tid);
+    L_PROF(7);
+    lstm_layer_forward(cluster, S, l, (int)input, sh, rank, tid, prof, tprev);
   }
   // ---- softmax layer: this CTA's rows of W_o[e] from HBM/L2 into shared memory, then 32 chains ----
   const int rpc = (V + LSTM_CTAS - 1) / LSTM_CTAS;                  // rows per CTA
@@ -197,9 +211,9 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   if (tid < nrow) {
     const float* wr = sh.pool + (size_t)tid * HW;
     float sum = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < HW; ++j) sum = XM_FADD(sum, XM_FMUL(sh.hid[j], wr[j]));
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) { float* rl = cluster.map_shared_rank(sh.logits, c); rl[r0 + tid] = sum; }
   }
   cluster.sync();
@@ -212,10 +226,11 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   if (tid == 0) { float m2 = 0.0f; for (int w = 0; w < LSTM_THREADS / 32; ++w) m2 = fmaxf(m2, sh.err[w]); sh.scal[4] = m2; }
   __syncthreads();
   const float max_out = sh.scal[4];
-  for (int i = tid; i < V; i += LSTM_THREADS) sh.logits[i] = xm_expf(XM_FSUB(sh.logits[i], max_out));
+  for (int i = tid; i < V; i += LSTM_THREADS) sh.logits[i] = lt_expf(XM_FSUB(sh.logits[i], max_out));
   __syncthreads();
   if (tid == 0) {
     float total = sh.logits[0];
+#pragma unroll 8
     for (int i = 1; i < V; ++i) total = XM_FADD(total, sh.logits[i]);
     sh.scal[5] = total;
   }
@@ -228,6 +243,7 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   if (rank == 0 && tid == 0) S.epoch = (e + 1 == LH) ? 0 : e + 1;
   __threadfence();
   cluster.sync();
+  L_PROF(6);
 }
 
 // One (epoch, layer) step of the error recursion (LstmLayer::BackwardPass, lstm-layer.cpp:108-197)
@@ -268,7 +284,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
     *gamma_u = XM_FADD(*gamma_u, XM_FMUL(e, n));
     escaled = XM_FMUL(e, XM_FMUL(G.gamma[cell], G.ivar[ep]));
     sh.nown[g][i] = n;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(sh.gat, c);
       rd[g][cell] = escaled;
@@ -280,6 +296,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
     float s = XM_FMUL(sh.gat[g][LC - 1], sh.gat2[g][LC - 1]);
+#pragma unroll 8
     for (int i = LC - 2; i >= 0; --i) s = XM_FADD(s, XM_FMUL(sh.gat[g][i], sh.gat2[g][i]));
     sh.scal[g] = XM_FDIV(s, (float)LC);
   }
@@ -289,7 +306,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
     const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
     const float e = XM_FSUB(escaled, XM_FMUL(sh.scal[g], sh.nown[g][i]));
     L.gate[g].err[(size_t)ep * LC + cell] = e;       // final gate error of this step
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(sh.gat2, c);
       rd[g][cell] = e;
@@ -362,7 +379,7 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int t
           for (int ep = LH - 1; ep >= 0; --ep) if (sh.sym[ep] == col) acc = XM_FADD(acc, es[ep * LCPC]);
         }
         GateState& G = L.gate[g];
-        const size_t idx = ((size_t)rank * row + col) * LCPC + i;
+        const size_t idx = lstm_widx(V, in_size, col, LCPC * rank + i);
         float m = G.m[idx], v = G.v[idx], w = G.w[idx];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
@@ -397,7 +414,8 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int t
 // ByteMixer::ByteUpdate -> Lstm::SetInput + Lstm::Perceive + Lstm::Predict (byte-mixer.cpp:22-38,
 // lstm.cpp:80-150) by the whole cluster. `ppmd` = 256-entry PPMD distribution after this byte (or
 // null), `byte` = the byte just completed. Leaves the new 256-entry distribution in S.bm.probs.
-__device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, const float* ppmd, u32 byte, LstmShared& sh, int rank, int tid) {
+__device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, const float* ppmd, u32 byte, LstmShared& sh, int rank, int tid,
+                                 unsigned long long* prof, long long* tprev) {
   const int V = S.V, HW = LSTM_HID;
   const unsigned input = (unsigned)S.byte_map[byte];
   const int epoch = S.epoch;
@@ -418,6 +436,7 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
   if (rank == 0 && tid == 0) S.input_history[last_epoch] = input;
   __threadfence();
   cluster.sync();
+  L_PROF(0);
   if (epoch == 0) {
     // ------------------------------ truncated BPTT ------------------------------
     if (tid < LH) sh.sym[tid] = tid == 0 ? old_input : (int)S.input_history[tid - 1];
@@ -430,12 +449,11 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
     rec[1] = sh.pool + 3 * 1 * LC * LCPC;               // layer 1: [3][2][LC][LCPC]
     float* wo_s = sh.pool + 3 * 3 * LC * LCPC;          // [V][LCPC] slice of W_o[ep] for the current layer
     for (int l = 0; l < 2; ++l) {
-      const int row = S.layer[l].in_size + V;
       const int ntypes = l + 1;                         // layer 0 has no layer below: only the stored_error block
       for (int k = tid; k < 3 * ntypes * LC * LCPC; k += LSTM_THREADS) {
         const int i = k % LCPC, j = (k / LCPC) % LC, type = (k / (LCPC * LC)) % ntypes, g = k / (LCPC * LC * ntypes);
         const int col = 2 * V + type * LC + LCPC * rank + i;
-        lcp_async4(rec[l] + k, S.layer[l].gate[g].w + lstm_widx(row, col, j));
+        lcp_async4(rec[l] + k, S.layer[l].gate[g].w + lstm_widx(V, S.layer[l].in_size, col, j));
       }
     }
     lcp_async_wait();
@@ -456,7 +474,7 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
         if (tid < LCPC) {
           float he = he_reg;
           const float* wc = wo_s + tid;
-#pragma unroll 4
+#pragma unroll 8
           for (int i = 0; i < V; ++i) he = XM_FADD(he, XM_FMUL(wc[(size_t)i * LCPC], sh.err[i]));
           he_reg = he;
         }
@@ -468,9 +486,11 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
       S.hidden_error[cell] = he_reg;
       for (int l = 0; l < 2; ++l) { S.layer[l].stored_error[cell] = stored_reg[l]; S.layer[l].state_error[cell] = se_reg[l]; }
     }
+    L_PROF(1);
     lstm_apply_updates(S, sh, rank, tid, gamma_u, beta_u);
     __threadfence();
     cluster.sync();
+    L_PROF(2);
   }
   // ---- output layer SGD (lstm.cpp:112-116): W_o[epoch] = W_o[last_epoch] - (lr*err_i) * hidden, own rows ----
   {
@@ -487,7 +507,8 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
     }
     __syncthreads();
   }
-  lstm_predict(cluster, S, input, sh, rank, tid);
+  L_PROF(3);
+  lstm_predict(cluster, S, input, sh, rank, tid, prof, tprev);
   // ByteMixer: scatter back to 256 bytes; ByteModel::ByteUpdate resets the range
   if (rank == 0) {
     if (tid < 256) S.bm.probs[tid] = S.vocab[tid] ? sh.logits[S.byte_map[tid]] : 0.0f;
@@ -518,18 +539,35 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
   const int tid = threadIdx.x;
+  unsigned long long* prof = (a.prof && rank == 0 && tid == 0) ? a.prof : nullptr;
+  long long tprev = clock64();
   for (u32 pos = 0; pos < a.n_bytes; ++pos) {
     const u32 byte = a.bytes[pos];
-    if (rank == 0 && tid == 0) {
-      for (int j = 7; j >= 0; --j) {
-        const u64 t = (u64)pos * 8 + (7 - j);
-        lstm_readout(S, T, &a.lstm_x[2 * t], &a.lstm_x[2 * t + 1]);
-        bm_perceive(S.bm, (byte >> j) & 1);
+    if (rank == 0) {
+      // ByteModel::Predict for the 8 bits of this byte (byte-model.cpp:8-24): the ranges are known, so
+      // the 8 read-outs are 8 independent serial sums out of shared memory, one lane each.
+      for (int i = tid; i < 256; i += LSTM_THREADS) sh.logits[i] = S.bm.probs[i];
+      __syncthreads();
+      if (tid < 8) {
+        int bot = 0, top = 255;
+        for (int k = 0; k < tid; ++k) { const int mid = bot + ((top - bot) / 2); if ((byte >> (7 - k)) & 1) bot = mid + 1; else top = mid; }
+        const int mid = bot + ((top - bot) / 2);
+        float num = 0.0f;
+#pragma unroll 8
+        for (int i = mid + 1; i <= top; ++i) num = XM_FADD(num, sh.logits[i]);
+        float denom = num;
+#pragma unroll 8
+        for (int i = bot; i <= mid; ++i) denom = XM_FADD(denom, sh.logits[i]);
+        const float p = denom == 0 ? 0.5f : XM_FDIV(num, denom);
+        const u64 t = (u64)pos * 8 + tid;
+        a.lstm_x[2 * t] = stretch(T, p);
+        a.lstm_x[2 * t + 1] = (p == 0.0f || p == 1.0f) ? p : -1.0f;
       }
+      __syncthreads();
     }
     __threadfence();
     cluster.sync();
-    lstm_byte_update(cluster, S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, rank, tid);
+    lstm_byte_update(cluster, S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, rank, tid, prof, &tprev);
   }
 }
 
@@ -545,7 +583,8 @@ lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd) {
   cgl::cluster_group cluster = cgl::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
-  lstm_byte_update(cluster, st->lstm, ppmd, byte, sh, (int)cluster.block_rank(), threadIdx.x);
+  long long tprev = 0;
+  lstm_byte_update(cluster, st->lstm, ppmd, byte, sh, (int)cluster.block_rank(), threadIdx.x, nullptr, &tprev);
 }
 
 #undef LC

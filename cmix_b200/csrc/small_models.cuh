@@ -75,8 +75,10 @@ __device__ __forceinline__ float stretch(const Tables& T, float p) {     // mixe
 __device__ float bytemodel_predict(const float* probs, int bot, int top, int* ex_out) {
   const int m = bot + ((top - bot) / 2);
   float num = 0.0f;
+#pragma unroll 8
   for (int i = m + 1; i <= top; ++i) num = XM_FADD(num, probs[i]);
   float denom = num;
+#pragma unroll 8
   for (int i = bot; i <= m; ++i) denom = XM_FADD(denom, probs[i]);
   int ex = bot; float best = probs[bot];
   for (int i = bot + 1; i <= top; ++i) if (probs[i] > best) { best = probs[i]; ex = i; }
@@ -340,8 +342,7 @@ __device__ void bracket_byte_update(SmallState& s, float* probs, u32 byte, int t
 }
 
 // One bit of Predict() for the small models: writes 54 stretched inputs + PPMD input + selectors.
-__device__ void small_predict(StreamState* st, const Tables& T, SmallShared& sh, float* out_x, u32* out_sel, int tid) {
-  SmallState& s = st->small;
+__device__ void small_predict(SmallState& s, const Tables& T, SmallShared& sh, float* out_x, u32* out_sel, int tid) {
   const LaneRole r = lane_role(tid);
   const u32 bc = sh.bit_context;
   float p = 0.5f; bool has = true;
@@ -364,8 +365,7 @@ __device__ void small_predict(StreamState* st, const Tables& T, SmallShared& sh,
 }
 
 // One bit of Perceive() for the small models, then contexts, then byte updates.
-__device__ void small_perceive(StreamState* st, SmallShared& sh, int bit, const float* ppmd_next, int pretrain, int tid, int nthreads) {
-  SmallState& s = st->small;
+__device__ void small_perceive(SmallState& s, SmallShared& sh, int bit, const float* ppmd_next, int pretrain, int tid, int nthreads) {
   const LaneRole r = lane_role(tid);
   const u32 bc = sh.bit_context;
   // --- Model::Perceive ---
@@ -443,13 +443,23 @@ __device__ void small_perceive(StreamState* st, SmallShared& sh, int bit, const 
 }
 
 // Bulk kernel: all bits of a chunk (compress direction: the bits are known).
+// The whole SmallState (68 KB: every model's adaptive tables, context registers and the POINTERS to
+// the big HBM tables) lives in shared memory for the duration of the kernel: a state machine that
+// chases `state->table_ptr` through HBM pays ~1 us per dependent load; out of shared memory it pays 30 ns.
 __global__ void __launch_bounds__(64, 1)
 small_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
   const ChunkArgs a = args_all[blockIdx.x];
   StreamState* st = a.st;
-  SmallState& s = st->small;
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  SmallState& s = *reinterpret_cast<SmallState*>(small_raw);
   __shared__ SmallShared sh;
   const int tid = threadIdx.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&st->small);
+    uint4* dst = reinterpret_cast<uint4*>(small_raw);
+    for (int i = tid; i < (int)(sizeof(SmallState) / 16); i += 64) dst[i] = src[i];
+  }
+  __syncthreads();
   for (int i = tid; i < 256; i += 64) { sh.bracket_probs[i] = s.bracket_bm.probs[i]; sh.ppmd_probs[i] = s.ppmd_bm.probs[i]; }
   if (tid == 0) small_refresh_tables(s, sh);
   __syncthreads();
@@ -458,13 +468,19 @@ small_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
     for (int j = 7; j >= 0; --j) {
       const u64 t = (u64)pos * 8 + (7 - j);
       const int bit = (byte >> j) & 1;
-      small_predict(st, T, sh, a.pretrain ? st->small_x : a.small_x + t * SMALL_X_PITCH,
+      small_predict(s, T, sh, a.pretrain ? st->small_x : a.small_x + t * SMALL_X_PITCH,
                     a.pretrain ? st->sel : a.sel + t * SEL_PITCH, tid);
       __syncthreads();
-      small_perceive(st, sh, bit, (j == 0 && a.ppmd) ? a.ppmd + (u64)pos * 256 : nullptr, (int)a.pretrain, tid, 64);
+      small_perceive(s, sh, bit, (j == 0 && a.ppmd) ? a.ppmd + (u64)pos * 256 : nullptr, (int)a.pretrain, tid, 64);
     }
   }
   for (int i = tid; i < 256; i += 64) { s.bracket_bm.probs[i] = sh.bracket_probs[i]; s.ppmd_bm.probs[i] = sh.ppmd_probs[i]; }
+  __syncthreads();
+  {
+    uint4* dst = reinterpret_cast<uint4*>(&st->small);
+    const uint4* src = reinterpret_cast<const uint4*>(small_raw);
+    for (int i = tid; i < (int)(sizeof(SmallState) / 16); i += 64) dst[i] = src[i];
+  }
 }
 
 // Lock-step halves (Predictor::Predict / Perceive called bit by bit from the host).
@@ -475,7 +491,7 @@ __global__ void __launch_bounds__(64, 1) small_predict_kernel(StreamState* st, T
   for (int i = tid; i < 256; i += 64) { sh.bracket_probs[i] = s.bracket_bm.probs[i]; sh.ppmd_probs[i] = s.ppmd_bm.probs[i]; }
   if (tid == 0) small_refresh_tables(s, sh);
   __syncthreads();
-  small_predict(st, T, sh, st->small_x, st->sel, tid);
+  small_predict(st->small, T, sh, st->small_x, st->sel, tid);
 }
 __global__ void __launch_bounds__(64, 1) small_perceive_kernel(StreamState* st, int bit, const float* ppmd_next, int pretrain) {
   __shared__ SmallShared sh;
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(64, 1) small_perceive_kernel(StreamState* st, 
   for (int i = tid; i < 256; i += 64) { sh.bracket_probs[i] = s.bracket_bm.probs[i]; sh.ppmd_probs[i] = s.ppmd_bm.probs[i]; }
   if (tid == 0) small_refresh_tables(s, sh);
   __syncthreads();
-  small_perceive(st, sh, bit, ppmd_next, pretrain, tid, 64);
+  small_perceive(st->small, sh, bit, ppmd_next, pretrain, tid, 64);
   for (int i = tid; i < 256; i += 64) { s.bracket_bm.probs[i] = sh.bracket_probs[i]; s.ppmd_bm.probs[i] = sh.ppmd_probs[i]; }
 }
 

@@ -73,7 +73,7 @@ struct MatchState { u64 history_pos, cur_match; u32* map; u64 map_size; int limi
 struct ByteModelState { int top, mid, bot, ex; float probs[256]; };
 struct IHashState { u64* hashes; u64 ctx1, ctx, size; u32 size1, h1, h2, pad; };
 
-struct SmallState {
+struct alignas(16) SmallState {
   // ContextManager scalars (context-manager.h:23-27)
   u32 bit_context, wrt_state;
   u64 long_bit_context, history_pos, line_break, longest_match, wrt_context;
@@ -94,6 +94,7 @@ struct SmallState {
   u8 vocab[256];
   u32 error;                    // sticky error flags (stack overflow etc.)
 };
+static_assert(sizeof(SmallState) % 16 == 0, "SmallState is copied to shared memory in 16-byte units");
 
 // ---- LSTM byte mixer (reference mixer/lstm.cpp, lstm-layer.cpp, byte-mixer.cpp) ----
 struct GateState {
