@@ -734,7 +734,7 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
     case CMIXB200_DBG_LSTM_PROBS: src = &P->d_st->lstm.bm.probs[0]; break;
     case CMIXB200_DBG_ERROR_FLAGS: src = &P->d_st->small.error; break;
     case CMIXB200_DBG_PROFILE:
-      if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 32 * 8)); CK(cudaMemset(P->d_prof, 0, 32 * 8)); }
+      if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 64 * 8)); CK(cudaMemset(P->d_prof, 0, 64 * 8)); }
       src = P->d_prof; break;
     default: g_last_error = "unknown debug id"; return CMIXB200_ERR_ARG;
   }

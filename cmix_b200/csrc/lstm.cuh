@@ -49,7 +49,23 @@ __host__ __device__ __forceinline__ size_t lstm_widx(int V, int in_size, int col
   return ((size_t)(cell / LCPC) * lstm_rowp(V, in_size) + pc) * LCPC + (cell % LCPC);
 }
 
+// Pointers and hot scalars of LstmState, copied into shared memory once per kernel: every
+// `state->array[...]` through HBM costs a dependent ~1 us load, and cluster barriers invalidate L1.
+struct LstmPtrs {
+  float* w[2][3]; float* m[2][3]; float* v[2][3]; float* state[2][3]; float* norm[2][3]; float* err[2][3]; float* ivar[2][3];
+  float* tanh_state[2]; float* igs[2]; float* last_state[2]; float* input[2];
+  float* out_w; float* output; const float* adam;
+  int in_size[2]; int lepoch[2]; int epoch; int V;
+  unsigned long long update_steps[2];
+};
+
 struct LstmShared {
+  LstmPtrs P;
+  float gam[2][3][LCPC], bet[2][3][LCPC];   // own cells: RMS-norm gain / bias
+  float cst[2][LCPC];                        // own cells: cell state
+  unsigned hist[LH];                         // Lstm::input_history_
+  int bmap[256]; unsigned char vocab[256];
+  float probs256[256];                       // byte-indexed distribution for the bit read-outs
   float in[2 * 256 + 2 * LC + 8];   // current layer input vector
   float gat[3][LC];                  // all-gathered per-gate vector (pre-activations / scaled errors)
   float gat2[3][LC];                 // all-gathered final gate errors
@@ -65,7 +81,7 @@ struct LstmShared {
 };
 
 #define L_PROF(slot) do { if (prof) { unsigned d_ = *reinterpret_cast<volatile unsigned*>(&sh.sym[0]), k_; \
-    asm volatile("mov.u32 %0, %1;" : "=r"(k_) : "r"(d_)); const long long n_ = clock64(); prof[slot] += (unsigned long long)(n_ - *tprev) + (k_ & 0u); *tprev = n_; } } while (0)
+    asm volatile("mov.u32 %0, %1;" : "=r"(k_) : "r"(d_)); const long long n_ = clock64(); prof[32 + (slot)] += (unsigned long long)(n_ - *tprev) + (k_ & 0u); *tprev = n_; } } while (0)
 
 __device__ __noinline__ float lt_tanhf(float x) { return xm_tanhf(x); }
 __device__ __noinline__ float lt_logistic(float x) { return xm_logistic(x); }
@@ -101,18 +117,18 @@ __device__ __forceinline__ void gather75(cgl::cluster_group& cluster, float (*ds
 // LstmLayer::ForwardPass (lstm-layer.cpp:62-99) for one layer; the whole cluster.
 __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, int l, int sym, LstmShared& sh, int rank, int tid,
                                    unsigned long long* prof, long long* tprev) {
-  LayerState& L = S.layer[l];
-  const int V = S.V, e = L.epoch, in_size = L.in_size;
-  const float* in_g = L.input + (size_t)e * in_size;
+  LstmPtrs& P = sh.P;
+  const int V = P.V, e = P.lepoch[l], in_size = P.in_size[l];
+  const float* in_g = P.input[l] + (size_t)e * in_size;
   // ---- stage: input vector + this CTA's weight slice (dense columns, then the symbol column) ----
   for (int j = tid; j < in_size; j += LSTM_THREADS) sh.in[j] = in_g[j];
   const int in_sizep = (in_size + 3) & ~3, rowp = lstm_rowp(V, in_size), gstride = (in_sizep + 4) * LCPC;
   for (int g = 0; g < 3; ++g) {
-    const float* src = L.gate[g].w + ((size_t)rank * rowp + lstm_vp(V)) * LCPC;     // dense columns, 16-byte aligned
+    const float* src = P.w[l][g] + ((size_t)rank * rowp + lstm_vp(V)) * LCPC;     // dense columns, 16-byte aligned
     float* dst = sh.pool + (size_t)g * gstride;
     const int n16 = in_sizep * LCPC / 4;
     for (int k = tid; k < n16; k += LSTM_THREADS) lcp_async16(dst + 4 * k, src + 4 * k);
-    const float* ssrc = L.gate[g].w + ((size_t)rank * rowp + sym) * LCPC;           // one-hot column `sym`
+    const float* ssrc = P.w[l][g] + ((size_t)rank * rowp + sym) * LCPC;           // one-hot column `sym`
     if (tid < LCPC) lcp_async4(dst + in_sizep * LCPC + tid, ssrc + tid);
   }
   lcp_async_wait();
@@ -143,41 +159,42 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
     for (int i = LC - 2; i >= 0; --i) ss = XM_FADD(ss, XM_FMUL(sh.gat[g][i], sh.gat[g][i]));
     const float iv = XM_FDIV(1.0f, __fsqrt_rn(XM_FADD(XM_FDIV(ss, (float)LC), 1e-5f)));
     sh.scal[g] = iv;
-    if (rank == 0) L.gate[g].ivar[e] = iv;
+    if (rank == 0) P.ivar[l][g][e] = iv;
   }
   __syncthreads();
+  L_PROF(9);
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
-    GateState& G = L.gate[g];
     const float n = XM_FMUL(sh.gat[g][cell], sh.scal[g]);
-    G.norm[(size_t)e * LC + cell] = n;
-    float s = XM_FADD(XM_FMUL(n, G.gamma[cell]), G.beta[cell]);
+    P.norm[l][g][(size_t)e * LC + cell] = n;
+    float s = XM_FADD(XM_FMUL(n, sh.gam[l][g][i]), sh.bet[l][g][i]);
     s = (g == 1) ? lt_tanhf(s) : lt_logistic(s);
-    G.state[(size_t)e * LC + cell] = s;
+    P.state[l][g][(size_t)e * LC + cell] = s;
     sh.act[g][i] = s;
   }
   __syncthreads();
+  L_PROF(10);
   if (tid < LCPC) {
     const int i = tid, cell = LCPC * rank + i;
     const float fs = sh.act[0][i], gs = sh.act[1][i], os = sh.act[2][i];
-    float c = L.state[cell];
-    L.last_state[(size_t)e * LC + cell] = c;
+    float c = sh.cst[l][i];
+    P.last_state[l][(size_t)e * LC + cell] = c;
     const float ig = XM_FSUB(1.0f, fs);
-    L.input_gate_state[(size_t)e * LC + cell] = ig;
+    P.igs[l][(size_t)e * LC + cell] = ig;
     c = XM_FMUL(c, fs);
     c = XM_FADD(c, XM_FMUL(gs, ig));
-    L.state[cell] = c;
+    sh.cst[l][i] = c;
     const float ts = lt_tanhf(c);
-    L.tanh_state[(size_t)e * LC + cell] = ts;
+    P.tanh_state[l][(size_t)e * LC + cell] = ts;
     const float h = XM_FMUL(os, ts);
-    S.hidden[l * LC + cell] = h;
 #pragma unroll 1
     for (int cc = 0; cc < LSTM_CTAS; ++cc) {
       float* rh = cluster.map_shared_rank(sh.hid, cc);
       rh[l * LC + cell] = h;
     }
   }
-  if (rank == 0 && tid == 0) L.epoch = (e + 1 == LH) ? 0 : e + 1;
+  __syncthreads();
+  if (tid == 0) P.lepoch[l] = (e + 1 == LH) ? 0 : e + 1;
   L_PROF(8);
   cluster.sync();
   L_PROF(7);
@@ -186,10 +203,10 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
 // Lstm::Predict (lstm.cpp:120-150)
 __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned input, LstmShared& sh, int rank, int tid,
                              unsigned long long* prof, long long* tprev) {
-  const int V = S.V, e = S.epoch, HW = LSTM_HID;
+  LstmPtrs& P = sh.P;
+  const int V = P.V, e = P.epoch, HW = LSTM_HID;
   for (int l = 0; l < 2; ++l) {
-    LayerState& L = S.layer[l];
-    float* in = L.input + (size_t)L.epoch * L.in_size;
+    float* in = P.input[l] + (size_t)P.lepoch[l] * P.in_size[l];
     // own h(t-1) into [V, V+200); layer 1 also gets layer 0's new h into [V+200, V+400)
     if (rank == 0) {
       if (tid < LC) in[V + tid] = sh.hid[l * LC + tid];
@@ -203,7 +220,7 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   // ---- softmax layer: this CTA's rows of W_o[e] from HBM/L2 into shared memory, then 32 chains ----
   const int rpc = (V + LSTM_CTAS - 1) / LSTM_CTAS;                  // rows per CTA
   const int r0 = rank * rpc, r1 = min(V, r0 + rpc);
-  const float* W = S.out_w + (size_t)e * V * HW;
+  const float* W = P.out_w + (size_t)e * V * HW;
   const int nrow = max(0, r1 - r0);
   for (int k = tid; k < nrow * HW; k += LSTM_THREADS) lcp_async4(sh.pool + k, W + (size_t)r0 * HW + k);
   lcp_async_wait();
@@ -238,9 +255,10 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   for (int i = tid; i < V; i += LSTM_THREADS) {
     const float o = XM_FDIV(sh.logits[i], sh.scal[5]);
     sh.logits[i] = o;
-    if (rank == 0) S.output[(size_t)e * V + i] = o;
+    if (rank == 0) P.output[(size_t)e * V + i] = o;
   }
-  if (rank == 0 && tid == 0) S.epoch = (e + 1 == LH) ? 0 : e + 1;
+  __syncthreads();
+  if (tid == 0) P.epoch = (e + 1 == LH) ? 0 : e + 1;
   __threadfence();
   cluster.sync();
   L_PROF(6);
@@ -252,14 +270,14 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
 //   rec[((g*ntypes + type)*LC + j)*LCPC + i] = W_g(cell j, column 2V + type*200 + (25*rank + i)), ntypes = l + 1
 __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, int l, int ep, LstmShared& sh, const float* rec,
                                     int rank, int tid, float* gamma_u, float* beta_u, float* he_reg, float* stored_reg, float* se_reg) {
-  LayerState& L = S.layer[l];
+  LstmPtrs& P = sh.P;
   const float kClip = 10.0f;
   float he = 0.0f, stored = 0.0f, se = 0.0f;
   if (tid < LCPC) {
     const int i = tid, cell = LCPC * rank + i;
     const size_t o = (size_t)ep * LC + cell;
-    const float ts = L.tanh_state[o], os = L.gate[2].state[o], gs = L.gate[1].state[o], fs = L.gate[0].state[o];
-    const float ig = L.input_gate_state[o], ls = L.last_state[o];
+    const float ts = P.tanh_state[l][o], os = P.state[l][2][o], gs = P.state[l][1][o], fs = P.state[l][0][o];
+    const float ig = P.igs[l][o], ls = P.last_state[l][o];
     he = *he_reg;
     if (ep == LH - 1) { stored = he; se = 0.0f; }
     else { stored = XM_FADD(*stored_reg, he); se = *se_reg; }
@@ -270,19 +288,18 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
     he = 0.0f;
     if (ep > 0) { se = XM_FMUL(se, fs); stored = 0.0f; }
   }
-  if (rank == 0 && tid == 0 && ep == 0) { if (L.update_steps < 3000) ++L.update_steps; }
+  if (tid == 0 && ep == 0) { if (P.update_steps[l] < 3000) ++P.update_steps[l]; }
   __syncthreads();
   // per gate: beta_u/gamma_u accumulation, scale by gamma*ivar, all-gather for the RMS-norm backward sum
   float escaled = 0.0f;
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
-    GateState& G = L.gate[g];
-    const float n = G.norm[(size_t)ep * LC + cell];
+    const float n = P.norm[l][g][(size_t)ep * LC + cell];
     float e = sh.eown[g][i];
     if (ep == LH - 1) { *gamma_u = 0.0f; *beta_u = 0.0f; }
     *beta_u = XM_FADD(*beta_u, e);
     *gamma_u = XM_FADD(*gamma_u, XM_FMUL(e, n));
-    escaled = XM_FMUL(e, XM_FMUL(G.gamma[cell], G.ivar[ep]));
+    escaled = XM_FMUL(e, XM_FMUL(sh.gam[l][g][i], P.ivar[l][g][ep]));
     sh.nown[g][i] = n;
 #pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
@@ -291,7 +308,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
     }
   }
   // the full norm vector of this step (for the sum) straight from HBM/L2 into shared memory
-  for (int k = tid; k < 3 * LC; k += LSTM_THREADS) sh.gat2[k / LC][k % LC] = L.gate[k / LC].norm[(size_t)ep * LC + (k % LC)];
+  for (int k = tid; k < 3 * LC; k += LSTM_THREADS) sh.gat2[k / LC][k % LC] = P.norm[l][k / LC][(size_t)ep * LC + (k % LC)];
   cluster.sync();
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
@@ -305,7 +322,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
     const float e = XM_FSUB(escaled, XM_FMUL(sh.scal[g], sh.nown[g][i]));
-    L.gate[g].err[(size_t)ep * LC + cell] = e;       // final gate error of this step
+    P.err[l][g][(size_t)ep * LC + cell] = e;         // final gate error of this step
 #pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(sh.gat2, c);
@@ -345,20 +362,20 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
 // Weight-gradient accumulation in the reference's time order + Adam (lstm-layer.cpp:11-32,182-196).
 // Each CTA owns its 25 cells: gate errors of all 100 steps in shared memory, inputs tiled by column.
 __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int tid, const float* gamma_u, const float* beta_u) {
-  const int V = S.V;
+  LstmPtrs& P = sh.P;
+  const int V = P.V;
   const float beta1 = 0.025f, beta2 = 0.9999f, eps = 1e-6f;
   enum { TILE = 128 };
   float* err_s = sh.pool;                         // [3][LH][LCPC]
   float* in_t = sh.pool + 3 * LH * LCPC;          // [LH][TILE]
   for (int l = 0; l < 2; ++l) {
-    LayerState& L = S.layer[l];
-    const float* ad = S.adam + 4 * L.update_steps;
+    const float* ad = P.adam + 4 * P.update_steps[l];
     const float alpha = ad[0], bc1 = ad[1], bc2 = ad[2];
-    const int in_size = L.in_size, row = in_size + V;
+    const int in_size = P.in_size[l], row = in_size + V;
     __syncthreads();
     for (int k = tid; k < 3 * LH * LCPC; k += LSTM_THREADS) {
       const int g = k / (LH * LCPC), r = k - g * LH * LCPC, ep = r / LCPC, i = r - ep * LCPC;
-      err_s[k] = L.gate[g].err[(size_t)ep * LC + LCPC * rank + i];
+      err_s[k] = P.err[l][g][(size_t)ep * LC + LCPC * rank + i];
     }
     for (int c0 = 0; c0 < row; c0 += TILE) {
       const int nc = min(TILE, row - c0);
@@ -366,7 +383,7 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int t
       // dense columns of this tile: inputs of all 100 steps
       for (int k = tid; k < LH * TILE; k += LSTM_THREADS) {
         const int ep = k / TILE, c = k - ep * TILE, col = c0 + c;
-        in_t[k] = (c < nc && col >= V) ? L.input[(size_t)ep * in_size + (col - V)] : 0.0f;
+        in_t[k] = (c < nc && col >= V) ? P.input[l][(size_t)ep * in_size + (col - V)] : 0.0f;
       }
       __syncthreads();
       for (int k = tid; k < 3 * nc * LCPC; k += LSTM_THREADS) {
@@ -378,33 +395,33 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int t
         } else {
           for (int ep = LH - 1; ep >= 0; --ep) if (sh.sym[ep] == col) acc = XM_FADD(acc, es[ep * LCPC]);
         }
-        GateState& G = L.gate[g];
         const size_t idx = lstm_widx(V, in_size, col, LCPC * rank + i);
-        float m = G.m[idx], v = G.v[idx], w = G.w[idx];
+        float* const Gm = P.m[l][g]; float* const Gv = P.v[l][g]; float* const Gw = P.w[l][g];
+        float m = Gm[idx], v = Gv[idx], w = Gw[idx];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
         w = XM_FSUB(w, XM_FMUL(alpha, XM_FDIV(XM_FDIV(m, bc1), __fsqrt_rn(XM_FADD(XM_FDIV(v, bc2), eps)))));
-        G.m[idx] = m; G.v[idx] = v; G.w[idx] = w;
+        Gm[idx] = m; Gv[idx] = v; Gw[idx] = w;
       }
     }
     if (tid < 96 && (tid & 31) < LCPC) {
       const int g = tid >> 5, cell = LCPC * rank + (tid & 31);
-      GateState& G = L.gate[g];
+      GateState& G = S.layer[l].gate[g];
       {
         const float acc = gamma_u[l];
-        float m = G.gamma_m[cell], v = G.gamma_v[cell], w = G.gamma[cell];
+        float m = G.gamma_m[cell], v = G.gamma_v[cell], w = sh.gam[l][g][tid & 31];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
         w = XM_FSUB(w, XM_FMUL(alpha, XM_FDIV(XM_FDIV(m, bc1), __fsqrt_rn(XM_FADD(XM_FDIV(v, bc2), eps)))));
-        G.gamma_m[cell] = m; G.gamma_v[cell] = v; G.gamma[cell] = w;
+        G.gamma_m[cell] = m; G.gamma_v[cell] = v; G.gamma[cell] = w; sh.gam[l][g][tid & 31] = w;
       }
       {
         const float acc = beta_u[l];
-        float m = G.beta_m[cell], v = G.beta_v[cell], w = G.beta[cell];
+        float m = G.beta_m[cell], v = G.beta_v[cell], w = sh.bet[l][g][tid & 31];
         m = XM_FMUL(m, beta1); m = XM_FADD(m, XM_FMUL(1.0f - beta1, acc));
         v = XM_FMUL(v, beta2); v = XM_FADD(v, XM_FMUL(XM_FMUL(1.0f - beta2, acc), acc));
         w = XM_FSUB(w, XM_FMUL(alpha, XM_FDIV(XM_FDIV(m, bc1), __fsqrt_rn(XM_FADD(XM_FDIV(v, bc2), eps)))));
-        G.beta_m[cell] = m; G.beta_v[cell] = v; G.beta[cell] = w;
+        G.beta_m[cell] = m; G.beta_v[cell] = v; G.beta[cell] = w; sh.bet[l][g][tid & 31] = w;
       }
     }
   }
@@ -414,32 +431,81 @@ __device__ void lstm_apply_updates(LstmState& S, LstmShared& sh, int rank, int t
 // ByteMixer::ByteUpdate -> Lstm::SetInput + Lstm::Perceive + Lstm::Predict (byte-mixer.cpp:22-38,
 // lstm.cpp:80-150) by the whole cluster. `ppmd` = 256-entry PPMD distribution after this byte (or
 // null), `byte` = the byte just completed. Leaves the new 256-entry distribution in S.bm.probs.
+// Load the pointer/scalar cache and this CTA's resident slices (kernel prologue) ...
+__device__ void lstm_load_cache(LstmState& S, LstmShared& sh, int rank, int tid) {
+  if (tid == 0) {
+    LstmPtrs& P = sh.P;
+    for (int l = 0; l < 2; ++l) {
+      LayerState& L = S.layer[l];
+      for (int g = 0; g < 3; ++g) {
+        GateState& G = L.gate[g];
+        P.w[l][g] = G.w; P.m[l][g] = G.m; P.v[l][g] = G.v; P.state[l][g] = G.state; P.norm[l][g] = G.norm; P.err[l][g] = G.err;
+        P.ivar[l][g] = G.ivar;
+      }
+      P.tanh_state[l] = L.tanh_state; P.igs[l] = L.input_gate_state; P.last_state[l] = L.last_state; P.input[l] = L.input;
+      P.in_size[l] = L.in_size; P.lepoch[l] = L.epoch; P.update_steps[l] = L.update_steps;
+    }
+    P.out_w = S.out_w; P.output = S.output; P.adam = S.adam; P.epoch = S.epoch; P.V = S.V;
+  }
+  if (tid < 96 && (tid & 31) < LCPC) {
+    const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
+    for (int l = 0; l < 2; ++l) { sh.gam[l][g][i] = S.layer[l].gate[g].gamma[cell]; sh.bet[l][g][i] = S.layer[l].gate[g].beta[cell]; }
+  }
+  if (tid < LCPC) { sh.cst[0][tid] = S.layer[0].state[LCPC * rank + tid]; sh.cst[1][tid] = S.layer[1].state[LCPC * rank + tid]; }
+  if (tid < LSTM_HORIZON) sh.hist[tid] = S.input_history[tid];
+  for (int i = tid; i < 256; i += LSTM_THREADS) { sh.bmap[i] = S.byte_map[i]; sh.vocab[i] = S.vocab[i]; sh.probs256[i] = S.bm.probs[i]; }
+  for (int j = tid; j < LSTM_HID; j += LSTM_THREADS) sh.hid[j] = S.hidden[j];
+  __syncthreads();
+  {   // softmax output of the previous byte (needed by the output-layer SGD)
+    const int V = sh.P.V, le = sh.P.epoch == 0 ? LSTM_HORIZON - 1 : sh.P.epoch - 1;
+    for (int i = tid; i < V; i += LSTM_THREADS) sh.logits[i] = sh.P.output[(size_t)le * V + i];
+  }
+  __syncthreads();
+}
+// ... and write the mutable part back (kernel epilogue).
+__device__ void lstm_store_cache(LstmState& S, LstmShared& sh, int rank, int tid) {
+  __syncthreads();
+  if (tid < LCPC) { S.layer[0].state[LCPC * rank + tid] = sh.cst[0][tid]; S.layer[1].state[LCPC * rank + tid] = sh.cst[1][tid]; }
+  if (rank == 0) {
+    if (tid == 0) {
+      for (int l = 0; l < 2; ++l) { S.layer[l].epoch = sh.P.lepoch[l]; S.layer[l].update_steps = sh.P.update_steps[l]; }
+      S.epoch = sh.P.epoch;
+    }
+    if (tid < LSTM_HORIZON) S.input_history[tid] = sh.hist[tid];
+    for (int j = tid; j < LSTM_HID; j += LSTM_THREADS) S.hidden[j] = sh.hid[j];
+    for (int i = tid; i < 256; i += LSTM_THREADS) S.bm.probs[i] = sh.probs256[i];
+    if (tid == 0) { S.bm.top = 255; S.bm.bot = 0; }
+  }
+}
+
+// ByteMixer::ByteUpdate -> Lstm::SetInput + Lstm::Perceive + Lstm::Predict (byte-mixer.cpp:22-38,
+// lstm.cpp:80-150) by the whole cluster. `ppmd` = 256-entry PPMD distribution after this byte (or
+// null), `byte` = the byte just completed. Leaves the new 256-entry distribution in sh.probs256.
 __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, const float* ppmd, u32 byte, LstmShared& sh, int rank, int tid,
                                  unsigned long long* prof, long long* tprev) {
-  const int V = S.V, HW = LSTM_HID;
-  const unsigned input = (unsigned)S.byte_map[byte];
-  const int epoch = S.epoch;
+  LstmPtrs& P = sh.P;
+  const int V = P.V, HW = LSTM_HID;
+  const unsigned input = (unsigned)sh.bmap[byte];
+  const int epoch = P.epoch;
   const int last_epoch = epoch == 0 ? LH - 1 : epoch - 1;
-  const int old_input = (int)S.input_history[last_epoch];
-  // hidden vector of the previous step, everywhere
-  for (int j = tid; j < HW; j += LSTM_THREADS) sh.hid[j] = S.hidden[j];
+  const int old_input = (int)sh.hist[last_epoch];
   // SetInput: aux[k] = 2 * ppmd[k-th vocabulary byte] into both layers' input at epoch_
-  if (rank == 0 && tid < 256 && S.vocab[tid]) {
+  if (rank == 0 && tid < 256 && sh.vocab[tid]) {
     const float p = ppmd ? ppmd[tid] : (float)(1. / 256);
     const float a = XM_FMUL(XM_FADD(0.0f, p), 2.0f);
-    const int k = S.byte_map[tid];
-    S.layer[0].input[(size_t)epoch * S.layer[0].in_size + k] = a;
-    S.layer[1].input[(size_t)epoch * S.layer[1].in_size + k] = a;
+    const int k = sh.bmap[tid];
+    P.input[0][(size_t)epoch * P.in_size[0] + k] = a;
+    P.input[1][(size_t)epoch * P.in_size[1] + k] = a;
   }
-  __threadfence();
-  cluster.sync();
-  if (rank == 0 && tid == 0) S.input_history[last_epoch] = input;
-  __threadfence();
-  cluster.sync();
+  __syncthreads();
+  if (tid == 0) sh.hist[last_epoch] = input;
+  __syncthreads();
   L_PROF(0);
   if (epoch == 0) {
     // ------------------------------ truncated BPTT ------------------------------
-    if (tid < LH) sh.sym[tid] = tid == 0 ? old_input : (int)S.input_history[tid - 1];
+    __threadfence();
+    cluster.sync();                                     // rank 0's SetInput writes are visible to every CTA
+    if (tid < LH) sh.sym[tid] = tid == 0 ? old_input : (int)sh.hist[tid - 1];
     float gamma_u[2] = {0.0f, 0.0f}, beta_u[2] = {0.0f, 0.0f};
     float he_reg = 0.0f, stored_reg[2] = {0.0f, 0.0f}, se_reg[2] = {0.0f, 0.0f};
     if (tid < LCPC) he_reg = S.hidden_error[LCPC * rank + tid];
@@ -453,15 +519,15 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
       for (int k = tid; k < 3 * ntypes * LC * LCPC; k += LSTM_THREADS) {
         const int i = k % LCPC, j = (k / LCPC) % LC, type = (k / (LCPC * LC)) % ntypes, g = k / (LCPC * LC * ntypes);
         const int col = 2 * V + type * LC + LCPC * rank + i;
-        lcp_async4(rec[l] + k, S.layer[l].gate[g].w + lstm_widx(V, S.layer[l].in_size, col, j));
+        lcp_async4(rec[l] + k, P.w[l][g] + lstm_widx(V, P.in_size[l], col, j));
       }
     }
     lcp_async_wait();
     __syncthreads();
     for (int ep = LH - 1; ep >= 0; --ep) {
-      const float* out = S.output + (size_t)ep * V;
-      const float* W = S.out_w + (size_t)ep * V * HW;
-      for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = ((unsigned)i == S.input_history[ep]) ? XM_FSUB(out[i], 1.0f) : out[i];
+      const float* out = P.output + (size_t)ep * V;
+      const float* W = P.out_w + (size_t)ep * V * HW;
+      for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = ((unsigned)i == sh.hist[ep]) ? XM_FSUB(out[i], 1.0f) : out[i];
       for (int l = 1; l >= 0; --l) {
         // slice of W_o[ep]: columns l*200 + own 25 cells, all V rows
         __syncthreads();
@@ -496,10 +562,10 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
   {
     const int rpc = (V + LSTM_CTAS - 1) / LSTM_CTAS;
     const int r0 = rank * rpc, r1 = min(V, r0 + rpc);
-    const float* out = S.output + (size_t)last_epoch * V;
-    const float* Wl = S.out_w + (size_t)last_epoch * V * HW;
-    float* We = S.out_w + (size_t)epoch * V * HW;
-    for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = XM_FMUL(0.03f, ((unsigned)i == input) ? XM_FSUB(out[i], 1.0f) : out[i]);
+    const float* Wl = P.out_w + (size_t)last_epoch * V * HW;
+    float* We = P.out_w + (size_t)epoch * V * HW;
+    // sh.logits still holds the softmax output of the previous byte (output_[last_epoch])
+    for (int i = tid; i < V; i += LSTM_THREADS) sh.err[i] = XM_FMUL(0.03f, ((unsigned)i == input) ? XM_FSUB(sh.logits[i], 1.0f) : sh.logits[i]);
     __syncthreads();
     for (int idx = r0 * HW + tid; idx < r1 * HW; idx += LSTM_THREADS) {
       const int i = idx / HW, j = idx - i * HW;
@@ -510,12 +576,8 @@ __device__ void lstm_byte_update(cgl::cluster_group& cluster, LstmState& S, cons
   L_PROF(3);
   lstm_predict(cluster, S, input, sh, rank, tid, prof, tprev);
   // ByteMixer: scatter back to 256 bytes; ByteModel::ByteUpdate resets the range
-  if (rank == 0) {
-    if (tid < 256) S.bm.probs[tid] = S.vocab[tid] ? sh.logits[S.byte_map[tid]] : 0.0f;
-    if (tid == 0) { S.bm.top = 255; S.bm.bot = 0; }
-  }
-  __threadfence();
-  cluster.sync();
+  if (tid < 256) sh.probs256[tid] = sh.vocab[tid] ? sh.logits[sh.bmap[tid]] : 0.0f;
+  __syncthreads();
 }
 
 // Bit-level read-out of the byte distribution (ByteModel::Predict + the override test of
@@ -541,34 +603,33 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
   const int tid = threadIdx.x;
   unsigned long long* prof = (a.prof && rank == 0 && tid == 0) ? a.prof : nullptr;
   long long tprev = clock64();
+  lstm_load_cache(S, sh, rank, tid);
   for (u32 pos = 0; pos < a.n_bytes; ++pos) {
     const u32 byte = a.bytes[pos];
     if (rank == 0) {
       // ByteModel::Predict for the 8 bits of this byte (byte-model.cpp:8-24): the ranges are known, so
       // the 8 read-outs are 8 independent serial sums out of shared memory, one lane each.
-      for (int i = tid; i < 256; i += LSTM_THREADS) sh.logits[i] = S.bm.probs[i];
-      __syncthreads();
       if (tid < 8) {
         int bot = 0, top = 255;
         for (int k = 0; k < tid; ++k) { const int mid = bot + ((top - bot) / 2); if ((byte >> (7 - k)) & 1) bot = mid + 1; else top = mid; }
         const int mid = bot + ((top - bot) / 2);
         float num = 0.0f;
 #pragma unroll 8
-        for (int i = mid + 1; i <= top; ++i) num = XM_FADD(num, sh.logits[i]);
+        for (int i = mid + 1; i <= top; ++i) num = XM_FADD(num, sh.probs256[i]);
         float denom = num;
 #pragma unroll 8
-        for (int i = bot; i <= mid; ++i) denom = XM_FADD(denom, sh.logits[i]);
+        for (int i = bot; i <= mid; ++i) denom = XM_FADD(denom, sh.probs256[i]);
         const float p = denom == 0 ? 0.5f : XM_FDIV(num, denom);
         const u64 t = (u64)pos * 8 + tid;
         a.lstm_x[2 * t] = stretch(T, p);
         a.lstm_x[2 * t + 1] = (p == 0.0f || p == 1.0f) ? p : -1.0f;
       }
-      __syncthreads();
     }
-    __threadfence();
-    cluster.sync();
     lstm_byte_update(cluster, S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, rank, tid, prof, &tprev);
   }
+  lstm_store_cache(S, sh, rank, tid);
+  __threadfence();
+  cluster.sync();
 }
 
 // Lock-step halves.
@@ -584,7 +645,12 @@ lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);
   long long tprev = 0;
-  lstm_byte_update(cluster, st->lstm, ppmd, byte, sh, (int)cluster.block_rank(), threadIdx.x, nullptr, &tprev);
+  const int rank = (int)cluster.block_rank();
+  lstm_load_cache(st->lstm, sh, rank, threadIdx.x);
+  lstm_byte_update(cluster, st->lstm, ppmd, byte, sh, rank, threadIdx.x, nullptr, &tprev);
+  lstm_store_cache(st->lstm, sh, rank, threadIdx.x);
+  __threadfence();
+  cluster.sync();
 }
 
 #undef LC

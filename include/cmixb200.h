@@ -79,7 +79,7 @@ void* cmixb200_mix_stream(cmixb200_predictor*);
 /* test hooks: copy intermediate arrays of the last bulk call to the host */
 enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, CMIXB200_DBG_LSTM_PROBS = 4,
        CMIXB200_DBG_ERROR_FLAGS = 5,
-       CMIXB200_DBG_PROFILE = 6 /* 32 u64 per-phase cycle counters; first fetch enables them */ };
+       CMIXB200_DBG_PROFILE = 6 /* 64 u64 per-phase cycle counters; first fetch enables them */ };
 int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
 
 #ifdef __cplusplus
