@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "1")), help="independent files per GPU")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "24")), help="independent files per GPU")
     ap.add_argument("--step-bytes", type=int, default=2048)
     ap.add_argument("--cpu-sample-bytes", type=int, default=4096)
     args = ap.parse_args()
@@ -193,11 +193,19 @@ def main():
     total_steps = K + W
     # ---- inputs resident in HBM before the timed region ----
     streams = []
+    free0 = torch.cuda.mem_get_info(dev)[0]
     for s in stream_block(S * world, world, rank):      # global stream ids owned by this rank (weak scaling: S per GPU)
         text, vocab, d_bytes, d_ext, d_ppmd = make_inputs(torch, dev, B * total_steps, seed=s)
         P = cmix_b200.Predictor(vocab, device=local_rank)
         d_out = torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)
         streams.append(dict(P=P, text=text, d_bytes=d_bytes, d_ext=d_ext, d_ppmd=d_ppmd, d_out=d_out))
+        if len(streams) == 1:
+            # every stream owns ~6 GB of model tables: refuse a stream count that cannot fit instead of running the box out of memory
+            per_stream = free0 - torch.cuda.mem_get_info(dev)[0] + 2 * 1024 * (8 * N_EXT * 2 + 256 * 4) + (64 << 20)
+            if per_stream * S > 0.94 * free0:
+                raise SystemExit("bench.py: %d streams x %.1f GB do not fit in %.0f GB of free HBM; lower --streams"
+                                 % (S, per_stream / 1e9, free0 / 1e9))
+            config["hbm_per_stream_gb"] = round(per_stream / 1e9, 2)
     torch.cuda.synchronize()
 
     def run_step(i):
@@ -236,33 +244,32 @@ def main():
     mix_ms, mix_n = streams[0]["P"].mix_kernel_ms()
     value = total_bytes / dt / 1e6
 
-    # ---- end to end through the C-ABI with host buffers (pinned), stream 0 of this rank ----
-    st0 = streams[0]
-    P0 = st0["P"]
-    n_e2e = min(K, 2)
+    # ---- end to end through the C-ABI with HOST (pinned) buffers: every stream of this rank, one more step ----
+    # The same predictors continue from where the device-resident run stopped; the step's inputs start in
+    # pinned host memory and its probabilities end there (cmixb200_code_batch stages them inside the call).
+    from cmix_b200.capi import code_batch
+    n_e2e = 1
     lo = (W + K - n_e2e) * B
-    h_bytes = torch.from_numpy(st0["text"][lo:lo + n_e2e * B].copy()).pin_memory()
-    h_ext = st0["d_ext"][lo * 8:(lo + n_e2e * B) * 8].cpu().pin_memory()
-    h_ppmd = st0["d_ppmd"][lo:lo + n_e2e * B].cpu().pin_memory()
-    # a fresh predictor so that the state matches nothing in particular; warm it with W steps of device data
-    Pe = cmix_b200.Predictor(np.bincount(st0["text"], minlength=256).clip(0, 1).astype(np.uint8), device=local_rank)
-    for i in range(W):
-        Pe.code_bytes_device(st0["d_bytes"][i * B:(i + 1) * B], B, st0["d_ext"][i * B * 8:(i + 1) * B * 8],
-                             st0["d_ppmd"][i * B:(i + 1) * B], st0["d_out"][i * B * 8:(i + 1) * B * 8])
+    h_bytes = [torch.from_numpy(st["text"][lo:lo + n_e2e * B].copy()).pin_memory() for st in streams]
+    h_ext = [st["d_ext"][lo * 8:(lo + n_e2e * B) * 8].cpu().pin_memory() for st in streams]
+    h_ppmd = [st["d_ppmd"][lo:lo + n_e2e * B].cpu().pin_memory() for st in streams]
+    h_out = [torch.empty(n_e2e * B * 8, dtype=torch.float32).pin_memory() for _ in streams]
     torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
     t0 = time.perf_counter()
-    for j in range(n_e2e):
-        p_host = Pe.code_bytes(h_bytes.numpy()[j * B:(j + 1) * B], h_ext.numpy().view(np.uint16)[j * B * 8:(j + 1) * B * 8],
-                               h_ppmd.numpy()[j * B:(j + 1) * B])
+    code_batch([st["P"] for st in streams], h_bytes, n_e2e * B, h_ext, h_ppmd, h_out)
+    torch.cuda.synchronize()
     dt_e2e = time.perf_counter() - t0
     if dist:
         tt = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt_e2e = float(tt.item())
-    e2e_value = n_e2e * B * world / dt_e2e / 1e6          # one stream per rank end to end
-    h2d = B + B * 8 * N_EXT * 2 + B * 256 * 4 + B * 8 * 4   # bytes + codes + PPMD + decay table
-    d2h = B * 8 * 4
-    Pe.close()
+    e2e_value = S * n_e2e * B * world / dt_e2e / 1e6
+    h2d = S * (B + B * 8 * N_EXT * 2 + B * 256 * 4 + B * 8 * 4)   # per rank: bytes + codes + PPMD + decay table
+    d2h = S * B * 8 * 4
+    if not all(bool(torch.isfinite(o).all()) and float(o.min()) >= 0.0 and float(o.max()) <= 1.0 for o in h_out):
+        raise SystemExit("bench.py: end-to-end probabilities out of range")
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
@@ -274,11 +281,12 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "one stream per rank through cmixb200_code_bytes (host buffers, copies in the timed region)"},
+                    "note": "all streams through cmixb200_code_batch with pinned host buffers; H2D of the step's inputs and D2H of its "
+                            "probabilities inside the timed region (bytes are per rank per step)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "mix_kernel_v2", "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
+                         "kernel": "mix_kernel_v3", "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
                          "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
                          "note": "serial-dependency bound: each dot product is one fp32 FADD chain (bit-exact parity)"},
             "bits_per_s": total_bytes * 8 / dt,

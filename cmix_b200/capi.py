@@ -54,6 +54,7 @@ def load_library():
     lib.cmixb200_code_bytes.argtypes = [vp, vp, c.c_size_t, vp, vp, vp]
     lib.cmixb200_code_bytes_device.argtypes = [vp, vp, c.c_size_t, vp, vp, vp]
     lib.cmixb200_code_batch_device.argtypes = [vp, c.c_int, vp, c.c_size_t, vp, vp, vp]
+    lib.cmixb200_code_batch.argtypes = [vp, c.c_int, vp, c.c_size_t, vp, vp, vp]
     lib.cmixb200_pretrain_bytes.argtypes = [vp, vp, c.c_size_t]
     lib.cmixb200_last_error.restype = c.c_char_p
     lib.cmixb200_kernel_launches.argtypes = [vp]
@@ -184,3 +185,20 @@ def code_batch_device(preds, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out):
     pp = VP(*[_ptr(t) for t in d_ppmd]) if d_ppmd is not None else None
     po = VP(*[_ptr(t) for t in d_p_out])
     _check(lib, lib.cmixb200_code_batch_device(hs, n, by, n_bytes, ex, pp, po), "code_batch_device")
+
+
+def code_batch(preds, bytes_, n_bytes, ext, ppmd, p_out):
+    """Host-buffer twin of code_batch_device: numpy arrays or pinned CPU torch tensors, one per predictor.
+
+    Inputs are staged to the device in double-buffered sub-steps inside the call; p_out[s] (float32,
+    n_bytes*8) receives what Predict() returned before each bit.
+    """
+    lib = load_library()
+    n = len(preds)
+    VP = ctypes.c_void_p * n
+    hs = VP(*[p._h.value for p in preds])
+    by = VP(*[_ptr(t) for t in bytes_])
+    ex = VP(*[_ptr(t) for t in ext]) if ext is not None else None
+    pp = VP(*[_ptr(t) for t in ppmd]) if ppmd is not None else None
+    po = VP(*[_ptr(t) for t in p_out])
+    _check(lib, lib.cmixb200_code_batch(hs, n, by, n_bytes, ex, pp, po), "code_batch")

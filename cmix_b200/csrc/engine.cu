@@ -264,6 +264,9 @@ struct cmixb200_predictor {
   size_t scratch_bits = 0;
   float* d_small_x = nullptr; u32* d_sel = nullptr; float* d_lstm_x = nullptr; float* d_decay = nullptr; float* d_p = nullptr;
   u8* d_bytes = nullptr; u16* d_ext = nullptr; float* d_ppmd = nullptr; size_t stage_bytes = 0;
+  // double-buffered host staging of the batch entry point
+  u8* d_bytes2[2] = {nullptr, nullptr}; u16* d_ext2[2] = {nullptr, nullptr}; float* d_ppmd2[2] = {nullptr, nullptr};
+  size_t stage2_bytes = 0; cudaStream_t s_copy = nullptr;
   // lock-step state
   u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
   u32 bit_context = 1;                 // partial byte incl. leading 1 (ContextManager::bit_context_)
@@ -609,6 +612,9 @@ void cmixb200_destroy(cmixb200_predictor* P) {
   for (void* q : {(void*)P->d_small_x, (void*)P->d_sel, (void*)P->d_lstm_x, (void*)P->d_decay, (void*)P->d_p,
                   (void*)P->d_bytes, (void*)P->d_ext, (void*)P->d_ppmd, (void*)P->d_args, (void*)P->d_ext_bit, (void*)P->d_ppmd_byte})
     if (q) cudaFree(q);
+  for (int k = 0; k < 2; ++k)
+    for (void* q : {(void*)P->d_bytes2[k], (void*)P->d_ext2[k], (void*)P->d_ppmd2[k]}) if (q) cudaFree(q);
+  if (P->s_copy) cudaStreamDestroy(P->s_copy);
   if (P->s_small) cudaStreamDestroy(P->s_small);
   if (P->s_lstm) cudaStreamDestroy(P->s_lstm);
   if (P->s_mix) cudaStreamDestroy(P->s_mix);
@@ -717,6 +723,55 @@ int cmixb200_pretrain_bytes(cmixb200_predictor* P, const uint8_t* bytes, size_t 
 int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes, size_t n_bytes,
                                const uint16_t* const* d_ext, const float* const* d_ppmd, float* const* d_p_out) {
   return RunPipelined(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, false);
+}
+
+int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t* const* bytes, size_t n_bytes,
+                        const uint16_t* const* ext, const float* const* ppmd, float* const* p_out) {
+  if (n_streams <= 0 || !preds || !bytes || !p_out) { g_last_error = "code_batch: bad arguments"; return CMIXB200_ERR_ARG; }
+  cmixb200_predictor* lead = preds[0];
+  CK(cudaSetDevice(lead->device));
+  const size_t kSub = 1024;     // staging granularity per stream: 1024 B of input = 33 MB of replayed codes
+  if (!lead->s_copy) CK(cudaStreamCreateWithFlags(&lead->s_copy, cudaStreamNonBlocking));
+  for (int s = 0; s < n_streams; ++s) {
+    cmixb200_predictor* P = preds[s];
+    if (P->device != lead->device) { g_last_error = "code_batch: all predictors must live on one device"; return CMIXB200_ERR_ARG; }
+    if (P->stage2_bytes < kSub) {
+      for (int k = 0; k < 2; ++k) {
+        CK(cudaMalloc(&P->d_bytes2[k], kSub));
+        CK(cudaMalloc(&P->d_ext2[k], kSub * 8 * N_EXT * 2));
+        CK(cudaMalloc(&P->d_ppmd2[k], kSub * 256 * 4));
+      }
+      P->stage2_bytes = kSub;
+    }
+    TRY(EnsureScratch(P, kSub));
+  }
+  auto stage = [&](size_t off, int k) -> int {
+    const size_t n = n_bytes - off < kSub ? n_bytes - off : kSub;
+    for (int s = 0; s < n_streams; ++s) {
+      cmixb200_predictor* P = preds[s];
+      CK(cudaMemcpyAsync(P->d_bytes2[k], bytes[s] + off, n, cudaMemcpyHostToDevice, lead->s_copy));
+      if (ext) CK(cudaMemcpyAsync(P->d_ext2[k], ext[s] + off * 8 * N_EXT, n * 8 * N_EXT * 2, cudaMemcpyHostToDevice, lead->s_copy));
+      if (ppmd) CK(cudaMemcpyAsync(P->d_ppmd2[k], ppmd[s] + off * 256, n * 256 * 4, cudaMemcpyHostToDevice, lead->s_copy));
+    }
+    return CMIXB200_OK;
+  };
+  std::vector<const uint8_t*> db(n_streams); std::vector<const uint16_t*> de(n_streams);
+  std::vector<const float*> dp(n_streams); std::vector<float*> dout(n_streams);
+  if (n_bytes) TRY(stage(0, 0));
+  int k = 0;
+  for (size_t off = 0; off < n_bytes; off += kSub, k ^= 1) {
+    const size_t n = n_bytes - off < kSub ? n_bytes - off : kSub;
+    CK(cudaStreamSynchronize(lead->s_copy));                      // stage(off) landed, previous results are on the host
+    if (off + kSub < n_bytes) TRY(stage(off + kSub, k ^ 1));      // next inputs travel while this sub-step computes
+    for (int s = 0; s < n_streams; ++s) {
+      db[s] = preds[s]->d_bytes2[k]; de[s] = preds[s]->d_ext2[k]; dp[s] = preds[s]->d_ppmd2[k]; dout[s] = preds[s]->d_p;
+    }
+    TRY(RunPipelined(preds, n_streams, db.data(), n, ext ? de.data() : nullptr, ppmd ? dp.data() : nullptr, dout.data(), false));
+    for (int s = 0; s < n_streams; ++s)
+      CK(cudaMemcpyAsync(p_out[s] + off * 8, preds[s]->d_p, n * 8 * 4, cudaMemcpyDeviceToHost, lead->s_copy));
+  }
+  CK(cudaStreamSynchronize(lead->s_copy));
+  return CMIXB200_OK;
 }
 
 unsigned long long cmixb200_kernel_launches(const cmixb200_predictor* P) { return P->launches; }

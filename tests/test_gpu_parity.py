@@ -152,6 +152,21 @@ def test_batch_of_streams_equals_individual_runs(cm):
         p.close()
 
 
+def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
+    """cmixb200_code_batch: host buffers, 1024-byte double-buffered staging; 1100 bytes per stream cross it."""
+    from cmix_b200.capi import code_batch
+    n = 1100
+    runs = [synthetic_streams(n, seed=s) for s in (31, 32)]
+    want = [port_replay(port, r[1], r[0], r[2], r[3]) for r in runs]
+    preds = [cm.Predictor(r[1]) for r in runs]
+    outs = [np.empty(n * 8, dtype=np.float32) for _ in runs]
+    code_batch(preds, [r[0] for r in runs], n, [r[2] for r in runs], [r[3] for r in runs], outs)
+    for p in preds:
+        p.close()
+    for o, w in zip(outs, want):
+        assert np.abs(o - w).max() <= TOL
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "oracle_dump")),
                     reason="oracle/_ref/oracle_dump not shipped")
 def test_fresh_reference_dump_on_this_box(cm, tmp_path):
