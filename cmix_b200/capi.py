@@ -55,6 +55,8 @@ def load_library():
     lib.cmixb200_code_bytes_device.argtypes = [vp, vp, c.c_size_t, vp, vp, vp]
     lib.cmixb200_code_batch_device.argtypes = [vp, c.c_int, vp, c.c_size_t, vp, vp, vp]
     lib.cmixb200_code_batch.argtypes = [vp, c.c_int, vp, c.c_size_t, vp, vp, vp]
+    lib.cmixb200_coder_begin.argtypes = [vp, c.c_size_t]
+    lib.cmixb200_coder_finish.argtypes = [vp, vp, c.c_size_t, c.POINTER(c.c_size_t)]
     lib.cmixb200_pretrain_bytes.argtypes = [vp, vp, c.c_size_t]
     lib.cmixb200_last_error.restype = c.c_char_p
     lib.cmixb200_kernel_launches.argtypes = [vp]
@@ -147,6 +149,18 @@ class Predictor:
         """All arguments are torch CUDA tensors (or None) already resident in HBM."""
         _check(self._lib, self._lib.cmixb200_code_bytes_device(self._h, _ptr(d_bytes), n_bytes, _ptr(d_ext), _ptr(d_ppmd),
                                                                 _ptr(d_p_out)), "code_bytes_device")
+
+    def coder_begin(self, capacity_bytes):
+        """Start the device arithmetic coder (Encoder, src/coder/encoder.cpp): bulk calls now also emit archive bytes."""
+        _check(self._lib, self._lib.cmixb200_coder_begin(self._h, int(capacity_bytes)), "coder_begin")
+        self._coder_cap = int(capacity_bytes)
+
+    def coder_finish(self):
+        """Encoder::Flush; returns the archive bytes (no runner.cpp header)."""
+        out = np.empty(self._coder_cap, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        _check(self._lib, self._lib.cmixb200_coder_finish(self._h, out.ctypes.data, out.size, ctypes.byref(n)), "coder_finish")
+        return out[:n.value].tobytes()
 
     def pretrain_bytes(self, data):
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))

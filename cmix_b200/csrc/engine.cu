@@ -25,6 +25,7 @@
 
 #include "../../include/cmixb200.h"
 #include "exact_math.h"
+#include "coder.cuh"
 #include "lstm.cuh"
 #include "mixer.cuh"
 #include "mixer_v2.cuh"
@@ -267,6 +268,8 @@ struct cmixb200_predictor {
   // double-buffered host staging of the batch entry point
   u8* d_bytes2[2] = {nullptr, nullptr}; u16* d_ext2[2] = {nullptr, nullptr}; float* d_ppmd2[2] = {nullptr, nullptr};
   size_t stage2_bytes = 0; cudaStream_t s_copy = nullptr;
+  // device arithmetic coder (compress direction)
+  CoderState* d_coder = nullptr; u8* d_code = nullptr; size_t code_cap = 0; bool coder_on = false;
   // lock-step state
   u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
   u32 bit_context = 1;                 // partial byte incl. leading 1 (ContextManager::bit_context_)
@@ -484,7 +487,7 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 }
 
 // Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
-int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain) {
+int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false) {
   const Tables T = g_tables.T;
   small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
   lead->launches++;
@@ -508,6 +511,7 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
     else mix_kernel_v3<<<2 * n_streams, MIX_THREADS, sizeof(MixShared3), lead->s_mix>>>(d_args, T);
     lead->launches++;
     if (lead->time_mix) { CK(cudaEventRecord(t1, lead->s_mix)); lead->pending_ev.push_back({t0, t1}); }
+    if (with_coder) { encode_kernel<<<n_streams, 32, 0, lead->s_mix>>>(d_args); lead->launches++; }
     CK(cudaEventDestroy(e1));
     CK(cudaEventDestroy(e2));
   }
@@ -527,6 +531,7 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   const size_t n_sub = pretrain ? 1 : (n_bytes + kSub - 1) / kSub;
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
+  bool any_coder = false;
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
     if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
@@ -547,6 +552,11 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
       a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
       a.lstm_x = P->d_lstm_x + off * 8 * 2;
       a.p_out = (d_p_out && d_p_out[s]) ? d_p_out[s] + off * 8 : nullptr;
+      if (P->coder_on && !pretrain) {
+        a.coder = P->d_coder;
+        if (!a.p_out) a.p_out = P->d_p + off * 8;        // the coder reads the probabilities from scratch
+        any_coder = true;
+      }
       a.n_bytes = (u32)n; a.pretrain = pretrain ? 1 : 0; a.prof = P->d_prof;
     }
   }
@@ -557,7 +567,7 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
     lead->n_args = args.size();
   }
   CK(cudaMemcpy(lead->d_args, args.data(), sizeof(ChunkArgs) * args.size(), cudaMemcpyHostToDevice));
-  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(lead, lead->d_args + k * n_streams, n_streams, pretrain));
+  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(lead, lead->d_args + k * n_streams, n_streams, pretrain, any_coder));
   CK(cudaStreamSynchronize(lead->s_small));
   if (!pretrain) {
     CK(cudaStreamSynchronize(lead->s_lstm));
@@ -614,6 +624,8 @@ void cmixb200_destroy(cmixb200_predictor* P) {
     if (q) cudaFree(q);
   for (int k = 0; k < 2; ++k)
     for (void* q : {(void*)P->d_bytes2[k], (void*)P->d_ext2[k], (void*)P->d_ppmd2[k]}) if (q) cudaFree(q);
+  if (P->d_coder) cudaFree(P->d_coder);
+  if (P->d_code) cudaFree(P->d_code);
   if (P->s_copy) cudaStreamDestroy(P->s_copy);
   if (P->s_small) cudaStreamDestroy(P->s_small);
   if (P->s_lstm) cudaStreamDestroy(P->s_lstm);
@@ -730,7 +742,7 @@ int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t
   if (n_streams <= 0 || !preds || !bytes || !p_out) { g_last_error = "code_batch: bad arguments"; return CMIXB200_ERR_ARG; }
   cmixb200_predictor* lead = preds[0];
   CK(cudaSetDevice(lead->device));
-  const size_t kSub = 1024;     // staging granularity per stream: 1024 B of input = 33 MB of replayed codes
+  const size_t kSub = 512;      // staging granularity per stream: 512 B of input = 16.6 MB of replayed codes
   if (!lead->s_copy) CK(cudaStreamCreateWithFlags(&lead->s_copy, cudaStreamNonBlocking));
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
@@ -771,6 +783,39 @@ int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t
       CK(cudaMemcpyAsync(p_out[s] + off * 8, preds[s]->d_p, n * 8 * 4, cudaMemcpyDeviceToHost, lead->s_copy));
   }
   CK(cudaStreamSynchronize(lead->s_copy));
+  return CMIXB200_OK;
+}
+
+int cmixb200_coder_begin(cmixb200_predictor* P, size_t capacity_bytes) {
+  CK(cudaSetDevice(P->device));
+  if (capacity_bytes == 0) { g_last_error = "coder_begin: zero capacity"; return CMIXB200_ERR_ARG; }
+  if (P->code_cap < capacity_bytes) {
+    if (P->d_code) cudaFree(P->d_code);
+    P->d_code = nullptr; P->code_cap = 0;
+    CK(cudaMalloc(&P->d_code, capacity_bytes));
+    P->code_cap = capacity_bytes;
+  }
+  if (!P->d_coder) CK(cudaMalloc(&P->d_coder, sizeof(CoderState)));
+  CoderState c; memset(&c, 0, sizeof c);
+  c.x1 = 0; c.x2 = 0xffffffffu; c.cap = capacity_bytes; c.out = P->d_code;
+  CK(cudaMemcpy(P->d_coder, &c, sizeof c, cudaMemcpyHostToDevice));
+  P->coder_on = true;
+  return CMIXB200_OK;
+}
+
+int cmixb200_coder_finish(cmixb200_predictor* P, uint8_t* out, size_t cap, size_t* n_out) {
+  CK(cudaSetDevice(P->device));
+  if (!P->coder_on) { g_last_error = "coder_finish without coder_begin"; return CMIXB200_ERR_ARG; }
+  encode_flush_kernel<<<1, 1, 0, P->s_mix>>>(P->d_coder);
+  P->launches++;
+  CK(cudaStreamSynchronize(P->s_mix));
+  CoderState c;
+  CK(cudaMemcpy(&c, P->d_coder, sizeof c, cudaMemcpyDeviceToHost));
+  P->coder_on = false;
+  if (n_out) *n_out = (size_t)c.n_out;
+  if (c.overflow) { g_last_error = "device coder: archive buffer too small"; return CMIXB200_ERR_ARG; }
+  if (c.n_out > cap) { g_last_error = "coder_finish: output buffer too small"; return CMIXB200_ERR_ARG; }
+  if (out && c.n_out) CK(cudaMemcpy(out, P->d_code, (size_t)c.n_out, cudaMemcpyDeviceToHost));
   return CMIXB200_OK;
 }
 

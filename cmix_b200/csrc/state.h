@@ -155,6 +155,14 @@ struct Tables {
 };
 
 // Per-launch arguments of the bulk kernels, one entry per stream.
+// Arithmetic coder state of one stream (coder.cuh), persistent across bulk calls.
+struct CoderState {
+  u32 x1, x2;                   // Encoder::x1_, x2_ (encoder.cpp:3-4)
+  u32 overflow, pad;
+  u64 n_out, cap;               // archive bytes produced / capacity of out
+  u8* out;
+};
+
 struct ChunkArgs {
   StreamState* st;
   const u8* bytes;              // [n_bytes] the coded stream
@@ -167,6 +175,7 @@ struct ChunkArgs {
   float* p_out;                 // [n_bytes*8] result
   u32 n_bytes;
   u32 pretrain;                 // 1: Pretrain() semantics (models + contexts only)
+  CoderState* coder;            // optional device arithmetic coder fed with (p_out, bit); null = off
   unsigned long long* prof;     // optional [32] per-phase SM-cycle accumulators (null = off)
 };
 

@@ -63,11 +63,18 @@ int cmixb200_code_bytes_device(cmixb200_predictor*, const uint8_t* d_bytes, size
 int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes,
                                size_t n_bytes, const uint16_t* const* d_ext, const float* const* d_ppmd,
                                float* const* d_p_out);
-/* The batch entry point with HOST buffers: inputs are staged to the device in 1024-byte sub-steps on a
+/* The batch entry point with HOST buffers: inputs are staged to the device in 512-byte sub-steps on a
  * copy stream, double buffered, so the transfer of sub-step k+1 overlaps the kernels of sub-step k; the
  * probabilities return to p_out[s] the same way. All predictors must live on one device. */
 int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t* const* bytes, size_t n_bytes,
                         const uint16_t* const* ext, const float* const* ppmd, float* const* p_out);
+/* Device arithmetic coder for the compress direction: replaces Encoder::Encode / Encoder::Flush
+ * (src/coder/encoder.cpp:14-39). Between begin and finish every bulk call (code_bytes*, code_batch*)
+ * also feeds its (probability, bit) pairs through the coder on the device; finish flushes and copies
+ * the archive bytes (without runner.cpp's header) to the HOST buffer `out`. capacity_bytes bounds the
+ * archive; overflow is reported by finish, never written past. */
+int cmixb200_coder_begin(cmixb200_predictor*, size_t capacity_bytes);
+int cmixb200_coder_finish(cmixb200_predictor*, uint8_t* out, size_t cap, size_t* n_out);
 /* preprocessor::Pretrain's loop (preprocessor.cpp:37-69) over a byte buffer (HOST). */
 int cmixb200_pretrain_bytes(cmixb200_predictor*, const uint8_t* bytes, size_t n_bytes);
 

@@ -153,7 +153,7 @@ def test_batch_of_streams_equals_individual_runs(cm):
 
 
 def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
-    """cmixb200_code_batch: host buffers, 1024-byte double-buffered staging; 1100 bytes per stream cross it."""
+    """cmixb200_code_batch: host buffers, 512-byte double-buffered staging; 1100 bytes per stream cross it twice."""
     from cmix_b200.capi import code_batch
     n = 1100
     runs = [synthetic_streams(n, seed=s) for s in (31, 32)]
@@ -165,6 +165,49 @@ def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
         p.close()
     for o, w in zip(outs, want):
         assert np.abs(o - w).max() <= TOL
+
+
+def test_device_coder_writes_the_reference_archive_bytes(cm, port, golden_text):
+    """Encoder::Encode/Flush on the device (coder.cuh): the archive body equals the host coder's over the
+    reference's own probabilities, across two bulk calls, and decodes back to the input bits."""
+    g = golden_text
+    bits = g.bits()
+    e = port.op_enc_create()
+    for pr, b in zip(g.p, bits):
+        port.op_enc_encode(e, float(pr), int(b))
+    buf = np.zeros(g.n_bytes * 2 + 64, dtype=np.uint8)
+    want = buf[:port.op_enc_finish(e, buf.ctypes.data, buf.size)].tobytes()
+    port.op_enc_destroy(e)
+    P = cm.Predictor(g.vocab)
+    P.coder_begin(g.n_bytes * 2 + 64)
+    n = 77
+    P.code_bytes(g.stream[:n], g.ext[:n * 8], g.ppmd[:n])
+    P.code_bytes(g.stream[n:], g.ext[n * 8:], g.ppmd[n:])
+    got = P.coder_finish()
+    assert got == want
+    assert len(got) < g.n_bytes
+    # a capacity that is too small is reported, not overrun
+    P2 = cm.Predictor(g.vocab)
+    P2.coder_begin(8)
+    P2.code_bytes(g.stream, g.ext, g.ppmd)
+    with pytest.raises(RuntimeError):
+        P2.coder_finish()
+    P2.close()
+    # decode with the GPU predictor in lock-step (Decoder::Decode, decoder.cpp:20-39)
+    coded = np.frombuffer(got, dtype=np.uint8).copy()
+    d = port.op_dec_create(coded.ctypes.data, coded.size)
+    D = cm.Predictor(g.vocab)
+    out = np.zeros_like(bits)
+    for t in range(bits.size):
+        D.feed_external_bit(g.ext[t])
+        b = port.op_dec_decode(d, D.Predict())
+        out[t] = b
+        if t % 8 == 7:
+            D.feed_external_byte(g.ppmd[t // 8])
+        D.Perceive(int(b))
+    port.op_dec_destroy(d)
+    D.close(); P.close()
+    assert np.array_equal(out, bits)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "oracle_dump")),
