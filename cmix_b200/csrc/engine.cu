@@ -527,7 +527,7 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   if (n_bytes == 0 || n_streams <= 0) return CMIXB200_OK;
   cmixb200_predictor* lead = preds[0];
   CK(cudaSetDevice(lead->device));
-  static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 512;
+  static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 128;
   const size_t n_sub = pretrain ? 1 : (n_bytes + kSub - 1) / kSub;
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
@@ -567,14 +567,25 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
     lead->n_args = args.size();
   }
   CK(cudaMemcpy(lead->d_args, args.data(), sizeof(ChunkArgs) * args.size(), cudaMemcpyHostToDevice));
-  for (size_t k = 0; k < n_sub; ++k) TRY(LaunchChunk(lead, lead->d_args + k * n_streams, n_streams, pretrain, any_coder));
-  CK(cudaStreamSynchronize(lead->s_small));
-  if (!pretrain) {
-    CK(cudaStreamSynchronize(lead->s_lstm));
-    CK(cudaStreamSynchronize(lead->s_mix));
-    for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
+  // Launch groups: each group of streams runs on the CUDA streams of its first predictor, so one group's mixer
+  // only waits for its own producers and the groups drift apart instead of moving in lock-step waves.
+  static const int kGroup = getenv("CMIXB200_GROUP") ? atoi(getenv("CMIXB200_GROUP")) : 8;
+  const int gsz = kGroup > 0 ? kGroup : n_streams;
+  for (size_t k = 0; k < n_sub; ++k)
+    for (int g0 = 0; g0 < n_streams; g0 += gsz) {
+      const int cnt = n_streams - g0 < gsz ? n_streams - g0 : gsz;
+      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder));
+    }
+  for (int g0 = 0; g0 < n_streams; g0 += gsz) {
+    cmixb200_predictor* G = preds[g0];
+    CK(cudaStreamSynchronize(G->s_small));
+    if (!pretrain) {
+      CK(cudaStreamSynchronize(G->s_lstm));
+      CK(cudaStreamSynchronize(G->s_mix));
+    }
+    HarvestMixTimes(G);
   }
-  HarvestMixTimes(lead);
+  if (!pretrain) for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
   return CMIXB200_OK;
 }
 
@@ -603,9 +614,15 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
   if (P->V == 0) { delete P; g_last_error = "empty vocabulary"; return CMIXB200_ERR_ARG; }
   int r = BuildStream(P);
   if (r == CMIXB200_OK) {
-    cudaStreamCreateWithFlags(&P->s_small, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&P->s_lstm, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&P->s_mix, cudaStreamNonBlocking);
+    // the mixer is the longest pole of the three and depends on both producers: when many streams
+    // oversubscribe the SMs its CTAs should be placed first, then the small models, then the LSTM clusters
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const bool use_prio = getenv("CMIXB200_NO_PRIORITY") == nullptr;
+    const int p_mix = use_prio ? prio_hi : 0, p_small = use_prio ? (prio_hi + 1 <= prio_lo ? prio_hi + 1 : prio_lo) : 0, p_lstm = use_prio ? prio_lo : 0;
+    cudaStreamCreateWithPriority(&P->s_small, cudaStreamNonBlocking, p_small);
+    cudaStreamCreateWithPriority(&P->s_lstm, cudaStreamNonBlocking, p_lstm);
+    cudaStreamCreateWithPriority(&P->s_mix, cudaStreamNonBlocking, p_mix);
     if (cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
         cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
   }
