@@ -28,7 +28,6 @@
 #include "coder.cuh"
 #include "lstm.cuh"
 #include "mixer.cuh"
-#include "mixer_v2.cuh"
 #include "mixer_v3.cuh"
 #include "small_models.cuh"
 #include "state.h"
@@ -242,7 +241,6 @@ int BuildSharedTables(int device) {
   CK(cudaMemcpyToSymbol(c_mixer_sel, msel, sizeof msel));
   CK(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallState)));
   CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
-  CK(cudaFuncSetAttribute(mix_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared2)));
   CK(cudaFuncSetAttribute(mix_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared3)));
   CK(cudaFuncSetAttribute(mix_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
@@ -503,11 +501,9 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
     CK(cudaStreamWaitEvent(lead->s_mix, e1, 0));
     CK(cudaStreamWaitEvent(lead->s_mix, e2, 0));
     static const bool use_v1 = getenv("CMIXB200_MIX_V1") != nullptr;   // barrier-per-phase reference version of the kernel
-    static const bool use_v2 = getenv("CMIXB200_MIX_V2") != nullptr;   // warp-specialised, SGD as a separate pass
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (lead->time_mix) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, lead->s_mix)); }
     if (use_v1) mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
-    else if (use_v2) mix_kernel_v2<<<2 * n_streams, MIX_THREADS, sizeof(MixShared2), lead->s_mix>>>(d_args, T);
     else mix_kernel_v3<<<2 * n_streams, MIX_THREADS, sizeof(MixShared3), lead->s_mix>>>(d_args, T);
     lead->launches++;
     if (lead->time_mix) { CK(cudaEventRecord(t1, lead->s_mix)); lead->pending_ev.push_back({t0, t1}); }

@@ -1,28 +1,34 @@
 // cmix_b200/csrc/mixer_v3.cuh
 //
-// Kernel "mix" v3 — same arithmetic as mixer.cuh / mixer_v2.cuh (which document the parity rules),
-// re-scheduled so that the per-bit critical loop of a CTA is ONLY
+// Kernel "mix" v3: the three-layer gated mixer + SSE of one stream for a whole sub-chunk of bits
+// (reference src/mixer/mixer.cpp:38-72, src/predictor.cpp:361-469, src/mixer/sse.cpp:243-328),
+// one thread-block cluster of 2 CTAs per stream, warp-specialised. Same arithmetic as mixer.cuh,
+// which documents the parity rules; this file is only about scheduling.
 //
-//     13 serial chains (with the previous bit's SGD step folded in)  ->  extra-input
-//     substitution  ->  coefficient  ->  next bit's chains.
+// Per bit, a CTA's critical loop is
+//     13 serial dot-product chains  ->  forward substitution through the extra inputs
+//     ->  SGD coefficient  ->  (movers) SGD step  ->  next bit's chains,
+// and the last arrow is pipelined: the 2104-float rows are cut into 8 chunks, the mover warps
+// apply bit t-1's step chunk by chunk and publish chunk_seq[c], and the chain warp starts bit t's
+// chain on chunk 0 as soon as that chunk carries the step - the update runs just ahead of the chain.
 //
-// * SGD is fused into the next dot product: when a mixer keeps its weight row, the chain lane
-//   computes w' = w - u_prev * x_prev on the fly, stores w' and uses it in the product
-//   (mixer.cpp:66-71 followed by :41-43 of the next bit; same fp32 operations, same order).
-//   Rows that are switched away get their pending update from the mover warps, off the critical
-//   path; the rare row whose 1024-step shrink is due, and single-buffered rows that switch at a
-//   byte boundary, are updated by the movers before the next chain starts.
-// * The movers (8 warps) plan bit t+1 while bit t's chains run: stage inputs (triple buffered),
-//   resolve rows, TMA-prefetch rows into spare buffers, pre-compute the step-dependent part of
-//   the learning rate (mixer.cpp:58-59, a double division) so that the chain warp's coefficient
-//   is one logistic + two multiplies.
-// * CTA 0 publishes each clamped output the moment it exists ("LL" 8-byte value+sequence slots),
-//   so CTA 1's extra-input prefix overlaps CTA 0's substitution loop.
-// * The T warp (layers 1/2, SSE, p_out) trails by up to 4 bits and is kept short: flat
-//   (row, column) work list for its SGD, step counters and rows resident, table look-ups for the
-//   next bit issued one bit ahead.
+// Warp roles (roles are pinned to schedulers: the arbiter prefers high warp ids):
+// * C warp (15): lanes 0..12 = the CTA's 13 layer-0 mixers. Chain out of shared memory with
+//   LDS.128 ping-pong buffers and packed FMUL2 products feeding one FADD chain per lane; then the
+//   triangular extra-input substitution; then u = decay*lr*(sigma(p)-bit) with decay*lr
+//   pre-computed by the movers (mixer.cpp:58-60).
+// * mover warps (11): while bit t's chains run they plan bit t+1 - stage the 2078 inputs (triple
+//   buffered, stretch LUT in shared memory), resolve every mixer's weight row, move rows whose
+//   selector changed with the TMA (cp.async.bulk + mbarrier; bit-level selectors own a spare
+//   buffer so the load never waits for the eviction), pre-compute the step-dependent learning
+//   rate - then apply bit t's SGD step chunk by chunk.
+// * T warp (14, CTA 0): layers 1 and 2, SSE and p_out, trailing by up to 4 bits behind a ring of
+//   {value, sequence} slots; rows resident per lane, SSE candidate buckets prefetched a bit ahead.
+// * CTA 0 publishes each clamped output the moment it exists (8-byte value+sequence "LL" slots
+//   through distributed shared memory), so CTA 1's extra-input prefix overlaps CTA 0's loop and no
+//   cluster barrier or cluster fence is ever executed inside the bit loop.
 #pragma once
-#include "mixer_v2.cuh"
+#include "mixer_prims.cuh"
 
 namespace cmixb200 {
 
@@ -34,7 +40,7 @@ struct MixShared3 {
   alignas(16) float rows[V3_NBUF][ROW_PITCH_S];
   alignas(16) float x[3][N_INPUTS + 2];
   // plan of bit t (parity t&1): movers -> chain warp
-  int plan_buf[2][16]; u32 plan_fuse[2][16]; float plan_dl[2][16]; u32 plan_shrink[2][16];
+  int plan_buf[2][16]; float plan_dl[2][16]; u32 plan_shrink[2][16];
   // results of bit t (parity t&1): chain warp -> movers
   float upd[2][16]; float cext[2][32];
   // mover bookkeeping
@@ -55,54 +61,6 @@ struct MixShared3 {
   unsigned short emap[T_ELEMS + 5];
   float lut12[4100];
 };
-
-// Serial dot product with the previous bit's SGD step folded in (see header). Branch-free so that
-// the 13 lanes never diverge and the loads software-pipeline: a lane with nothing pending runs the
-// same code with u = 0 (w - 0*x == w for every w; only the sign of an exact zero weight could differ,
-// and a zero weight contributes +-0 to a sum that starts at +0, which is unobservable).
-__device__ __forceinline__ float chain_fused(const float* __restrict__ x, float* __restrict__ row, float u,
-                                             const float* __restrict__ xp) {
-  const float4* x4 = reinterpret_cast<const float4*>(x);
-  const float4* p4 = reinterpret_cast<const float4*>(xp);
-  float4* w4 = reinterpret_cast<float4*>(row);
-  float p = 0.0f;
-  float4 xa[2], wa[2], qa[2], xb[2], wb[2], qb[2];
-#define CF_LOAD(X, W, Q, blk) { _Pragma("unroll") for (int q_ = 0; q_ < 2; ++q_) { X[q_] = x4[(blk) * 2 + q_]; W[q_] = w4[(blk) * 2 + q_]; Q[q_] = p4[(blk) * 2 + q_]; } }
-#define CF_EAT(X, W, Q, blk) { _Pragma("unroll") for (int q_ = 0; q_ < 2; ++q_) { \
-    float4 w_ = W[q_]; \
-    w_.x = XM_FSUB(w_.x, XM_FMUL(u, Q[q_].x)); w_.y = XM_FSUB(w_.y, XM_FMUL(u, Q[q_].y)); \
-    w_.z = XM_FSUB(w_.z, XM_FMUL(u, Q[q_].z)); w_.w = XM_FSUB(w_.w, XM_FMUL(u, Q[q_].w)); \
-    w4[(blk) * 2 + q_] = w_; \
-    p = XM_FADD(p, XM_FMUL(X[q_].x, w_.x)); p = XM_FADD(p, XM_FMUL(X[q_].y, w_.y)); \
-    p = XM_FADD(p, XM_FMUL(X[q_].z, w_.z)); p = XM_FADD(p, XM_FMUL(X[q_].w, w_.w)); } }
-  CF_LOAD(xa, wa, qa, 0);
-#pragma unroll 1
-  for (int b = 0; b < 258; b += 2) {             // blocks of 2 float4: 0..258 (259 blocks = 518 float4)
-    CF_LOAD(xb, wb, qb, b + 1);
-    CF_EAT(xa, wa, qa, b);
-    CF_LOAD(xa, wa, qa, b + 2);
-    CF_EAT(xb, wb, qb, b + 1);
-  }
-  CF_EAT(xa, wa, qa, 258);
-#undef CF_LOAD
-#undef CF_EAT
-  {                                               // float4 #518 and the two scalars 2076, 2077
-    const float4 a = x4[518], q = p4[518];
-    float4 w = w4[518];
-    w.x = XM_FSUB(w.x, XM_FMUL(u, q.x)); w.y = XM_FSUB(w.y, XM_FMUL(u, q.y));
-    w.z = XM_FSUB(w.z, XM_FMUL(u, q.z)); w.w = XM_FSUB(w.w, XM_FMUL(u, q.w));
-    w4[518] = w;
-    p = XM_FADD(p, XM_FMUL(a.x, w.x)); p = XM_FADD(p, XM_FMUL(a.y, w.y));
-    p = XM_FADD(p, XM_FMUL(a.z, w.z)); p = XM_FADD(p, XM_FMUL(a.w, w.w));
-  }
-#pragma unroll
-  for (int k = 2076; k < N_INPUTS; ++k) {
-    const float w = XM_FSUB(row[k], XM_FMUL(u, xp[k]));
-    row[k] = w;
-    p = XM_FADD(p, XM_FMUL(x[k], w));
-  }
-  return p;
-}
 
 enum { V3_CHUNKS = 8, V3_CHUNK4 = 64 };          // 8 chunks of 64 float4; the last also takes float4 512..518 and the scalar tail
 
@@ -202,7 +160,7 @@ __device__ __forceinline__ void movers_update(MixShared3& sh, int m0, int mtid, 
   }
 }
 
-// movers: run sh.jobs through the TMA (same protocol as mixer_v2.cuh::run_row_jobs)
+// movers: run sh.jobs through the TMA (same protocol as mixer_prims.cuh::run_row_jobs)
 __device__ __forceinline__ void run_row_jobs3(MixShared3& sh, StreamState* st, int m0, int mtid) {
   const int nj = sh.n_jobs;
   if (nj == 0) return;
@@ -414,12 +372,10 @@ mix_kernel_v3(const ChunkArgs* __restrict__ args_all, Tables T) {
             if (sh.tag[cur] == s) {
               sh.kind[i] = K_SAME;
               sh.plan_buf[par][i] = cur;
-              sh.plan_fuse[par][i] = 0;
               if (t > 0) sh.mupd[i] = cur;          // applied chunk by chunk just ahead of the chain
             } else if (alt >= 0) {
               sh.kind[i] = K_SWAP;
               sh.plan_buf[par][i] = alt;
-              sh.plan_fuse[par][i] = 0;
               if (t > 0) sh.mupd[i] = cur;          // its pending step is applied by the movers, off the critical path
               if (sh.tag[alt] != s) {
                 RowJob jb; jb.buf = alt; jb.mixer = i; jb.load_slot = s; jb.evict_slot = sh.tag[alt];
@@ -431,7 +387,6 @@ mix_kernel_v3(const ChunkArgs* __restrict__ args_all, Tables T) {
               sh.kind[i] = K_LATE_SWITCH;
               ++nlate;
               sh.plan_buf[par][i] = cur;
-              sh.plan_fuse[par][i] = 0;
             }
           }
           sh.n_jobs = nj; sh.n_late = nlate;
