@@ -242,7 +242,7 @@ int BuildSharedTables(int device) {
   CK(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallState)));
   CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(mix_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared3)));
-  CK(cudaFuncSetAttribute(mix_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
+  CK(cudaFuncSetAttribute(mix_predict_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   g_tables.ready = true;
@@ -267,6 +267,7 @@ struct cmixb200_predictor {
   u8* d_bytes2[2] = {nullptr, nullptr}; u16* d_ext2[2] = {nullptr, nullptr}; float* d_ppmd2[2] = {nullptr, nullptr};
   size_t stage2_bytes = 0; cudaStream_t s_copy = nullptr;
   // device arithmetic coder (compress direction)
+  cudaEvent_t ev_lock_mix = nullptr, ev_lock_small = nullptr;   // lock-step: order the two library streams per bit
   CoderState* d_coder = nullptr; u8* d_code = nullptr; size_t code_cap = 0; bool coder_on = false;
   // lock-step state
   u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
@@ -531,6 +532,8 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
     if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
+    CK(cudaStreamSynchronize(P->s_mix));                 // a lock-step Perceive() may still be in flight
+    CK(cudaStreamSynchronize(P->s_small));
     TRY(EnsureScratch(P, n_bytes));
     if (!pretrain) {
       FillDecay(decay, P->bits_done, n_bytes * 8);
@@ -619,6 +622,9 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
     cudaStreamCreateWithPriority(&P->s_small, cudaStreamNonBlocking, p_small);
     cudaStreamCreateWithPriority(&P->s_lstm, cudaStreamNonBlocking, p_lstm);
     cudaStreamCreateWithPriority(&P->s_mix, cudaStreamNonBlocking, p_mix);
+    cudaEventCreateWithFlags(&P->ev_lock_mix, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_lock_small, cudaEventDisableTiming);
+    cudaEventRecord(P->ev_lock_mix, P->s_mix);
     if (cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
         cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
   }
@@ -637,6 +643,8 @@ void cmixb200_destroy(cmixb200_predictor* P) {
     if (q) cudaFree(q);
   for (int k = 0; k < 2; ++k)
     for (void* q : {(void*)P->d_bytes2[k], (void*)P->d_ext2[k], (void*)P->d_ppmd2[k]}) if (q) cudaFree(q);
+  if (P->ev_lock_mix) cudaEventDestroy(P->ev_lock_mix);
+  if (P->ev_lock_small) cudaEventDestroy(P->ev_lock_small);
   if (P->d_coder) cudaFree(P->d_coder);
   if (P->d_code) cudaFree(P->d_code);
   if (P->s_copy) cudaStreamDestroy(P->s_copy);
@@ -662,13 +670,18 @@ int cmixb200_feed_external_byte(cmixb200_predictor* P, const float* ppmd256) {
 float cmixb200_predict(cmixb200_predictor* P) {
   const Tables T = g_tables.T;
   if (cudaSetDevice(P->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1.0f; }
-  small_predict_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, T);
-  lstm_predict_kernel<<<1, 32, 0, P->s_mix>>>(P->d_st, T);
-  mix_predict_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T, P->ext_bit_valid ? P->d_ext_bit : nullptr);
+  // 3 launches: producers (small models || LSTM read-out), 26 row CTAs (one serial chain each), final stage
+  // the producers run on s_small (behind the previous small_perceive), after the previous bit's mixer/LSTM update
+  if (cudaStreamWaitEvent(P->s_small, P->ev_lock_mix, 0) != cudaSuccess) { g_last_error = "predict: event wait failed"; return -1.0f; }
+  lock_predict_inputs_kernel<<<2, 64, 0, P->s_small>>>(P->d_st, T);
+  cudaEventRecord(P->ev_lock_small, P->s_small);
+  cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0);
+  mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, P->ext_bit_valid ? P->d_ext_bit : nullptr);
+  mix_predict_final_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T);
   P->launches += 3;
   float p = -1.0f;
   cudaError_t e = cudaMemcpyAsync(&p, &P->d_st->last_p, 4, cudaMemcpyDeviceToHost, P->s_mix);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
   if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
   P->ext_bit_valid = false;
   return p;
@@ -681,13 +694,14 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   const u32 full = (P->bit_context * 2 + bit) & 255;
   const float* ppmd = (byte_done && P->ppmd_byte_valid) ? P->d_ppmd_byte : nullptr;
   float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
-  small_perceive_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, bit, ppmd, 0);
-  mix_perceive_kernel<<<1, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
-  lstm_bit_kernel<<<1, 32, 0, P->s_mix>>>(P->d_st, bit);
+  // queued, not awaited: the host goes back to the arithmetic coder while the update runs; the next
+  // Predict() (same CUDA stream) is ordered behind it
+  small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, ppmd, 0);      // concurrent with the mixer / LSTM update
+  mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
   if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
-  P->launches += 3;
+  CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
+  P->launches += 2;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(P->s_mix));
   P->bits_done++;
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   if (byte_done) P->ppmd_byte_valid = false;
@@ -699,11 +713,10 @@ int cmixb200_pretrain(cmixb200_predictor* P, int bit) {
   bit = bit ? 1 : 0;
   const Tables T = g_tables.T;
   const bool byte_done = P->bit_context >= 128;
-  small_predict_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, T);
-  small_perceive_kernel<<<1, 64, 0, P->s_mix>>>(P->d_st, bit, nullptr, 1);
+  small_predict_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, T);
+  small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, nullptr, 1);
   P->launches += 2;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(P->s_mix));
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   return CMIXB200_OK;
 }
@@ -839,6 +852,8 @@ void* cmixb200_mix_stream(cmixb200_predictor* P) { return (void*)P->s_mix; }
 
 int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t bytes) {
   CK(cudaSetDevice(P->device));
+  CK(cudaStreamSynchronize(P->s_mix));
+  CK(cudaStreamSynchronize(P->s_small));
   const void* src = nullptr;
   switch (what) {
     case CMIXB200_DBG_SMALL_X: src = P->d_small_x; break;

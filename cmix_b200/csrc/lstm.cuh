@@ -633,11 +633,20 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
 }
 
 // Lock-step halves.
-__global__ void lstm_predict_kernel(StreamState* st, Tables T) {
-  if (threadIdx.x == 0) lstm_readout(st->lstm, T, &st->lstm_x, &st->lstm_override);
-}
-__global__ void lstm_bit_kernel(StreamState* st, int bit) {
-  if (threadIdx.x == 0) bm_perceive(st->lstm.bm, bit);
+// Lock-step Predict(), producer half: CTA 0 = the 54 small models + contexts (small_models.cuh), CTA 1 = the
+// LSTM's bit read-out (ByteModel::Predict, byte-model.cpp:8-15). Independent of each other, one launch.
+__global__ void __launch_bounds__(64, 1) lock_predict_inputs_kernel(StreamState* st, Tables T) {
+  if (blockIdx.x == 1) {
+    if (threadIdx.x == 0) lstm_readout(st->lstm, T, &st->lstm_x, &st->lstm_override);
+    return;
+  }
+  __shared__ SmallShared sh;
+  SmallState& s = st->small;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256; i += 64) { sh.bracket_probs[i] = s.bracket_bm.probs[i]; sh.ppmd_probs[i] = s.ppmd_bm.probs[i]; }
+  if (tid == 0) small_refresh_tables(s, sh);
+  __syncthreads();
+  small_predict(st->small, T, sh, st->small_x, st->sel, tid);
 }
 __global__ void __cluster_dims__(LSTM_CTAS, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd) {

@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 
 #include "exact_math.h"
+#include "lstm.cuh"
 #include "small_models.cuh"
 #include "state.h"
 
@@ -425,17 +426,53 @@ mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
 // Same arithmetic as mix_kernel; intermediate vectors are parked in StreamState.
 namespace cmixb200 {
 
+// ---------------------------------------------------------------------------------------------
+// Lock-step halves (Predict() / Perceive(bit) one bit at a time: the decoder's order). Nothing can
+// stay resident between the two calls, so the work is spread over SMs instead: one CTA per layer-0
+// mixer for the 26 serial chains and for the 26 row updates, one CTA for layers 1-2 + SSE.
+//
+// mix_predict_rows_kernel<<<26, 256>>>: CTA i stages the 2078 inputs, resolves mixer i's row
+// (mixer 12's selector is the auxiliary context of the staged inputs, predictor.cpp:388-393),
+// copies the row into shared memory and runs its chain on one thread (Mixer::Mix, mixer.cpp:41-43).
+struct LockRowShared {
+  alignas(16) float x[N_INPUTS + 2];
+  alignas(16) float row[ROW_PITCH_L0];
+  u32 slot;
+};
+
+__global__ void __launch_bounds__(256, 1)
+mix_predict_rows_kernel(StreamState* st, Tables T, const u16* ext /* device, N_EXT codes or null */) {
+  __shared__ LockRowShared sh;
+  const int tid = threadIdx.x, i = blockIdx.x;
+  stage_inputs(sh.x, T, ext, st->small_x, st->lstm_x, tid, 256);
+  __syncthreads();
+  if (tid == 0) {
+    const u32 sel = i == 12 ? aux_context(sh.x) : st->sel[i];
+    const u32 s = resolve_slot(st->mixer[i], sel);
+    st->slot[i] = s;
+    sh.slot = s;
+  }
+  __syncthreads();
+  {
+    const float4* g = reinterpret_cast<const float4*>(st->mixer[i].rows + (size_t)sh.slot * ROW_PITCH_L0);
+    float4* d = reinterpret_cast<float4*>(sh.row);
+    for (int k = tid; k < ROW_PITCH_L0 / 4; k += 256) d[k] = g[k];
+  }
+  if (i == 0) for (int k = tid; k < N_INPUTS; k += 256) st->x[k] = sh.x[k];
+  __syncthreads();
+  if (tid == 0) st->mains[i] = chain_l0(sh.x, sh.row);
+}
+
+// mix_predict_final_kernel<<<1, 512>>>: extra-input substitution, layers 1-2, SSE (mixer.cpp:45-53,
+// predictor.cpp:394-418, sse.cpp:243-289) from the 26 main sums.
 __global__ void __launch_bounds__(MIX_THREADS, 1)
-mix_predict_kernel(StreamState* st, Tables T, const u16* ext /* device, N_EXT codes or null */) {
+mix_predict_final_kernel(StreamState* st, Tables T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MixShared& sh = *reinterpret_cast<MixShared*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  stage_inputs(sh.x, T, ext, st->small_x, st->lstm_x, tid, MIX_THREADS);
-  if (tid < SEL_PITCH) sh.sel[tid] = tid < N_MIXERS ? st->sel[tid] : 0;
-  __syncthreads();
-  if (tid == 0) sh.sel[12] = aux_context(sh.x);
-  __syncthreads();
-  if (tid < N_MIXERS) { const u32 s = resolve_slot(st->mixer[tid], sh.sel[tid]); st->slot[tid] = s; if (tid >= N_L0) sh.slot1[tid - N_L0] = s; }
+  if (tid < N_L0) sh.mains[tid] = st->mains[tid];
+  if (tid >= 32 && tid < 35) { const int idx = tid == 32 ? 433 : (tid == 33 ? 2024 : 2077); sh.x[idx] = st->x[idx]; }
+  if (tid >= N_L0 && tid < N_MIXERS) { const u32 s = resolve_slot(st->mixer[tid], st->sel[tid]); st->slot[tid] = s; sh.slot1[tid - N_L0] = s; }
   __syncthreads();
   for (int k = tid; k < N_L1 * ROW_PITCH_L1; k += MIX_THREADS) {
     const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
@@ -446,39 +483,50 @@ mix_predict_kernel(StreamState* st, Tables T, const u16* ext /* device, N_EXT co
     const int i = k / N_L0, c = k - i * N_L0;
     sh.we[i][c] = st->mixer[i].rows[(size_t)st->slot[i] * ROW_PITCH_L0 + N_INPUTS + c];
   }
-  if (warp == 0 && lane < N_L0)
-    sh.mains[lane] = chain_l0(sh.x, st->mixer[lane].rows + (size_t)st->slot[lane] * ROW_PITCH_L0);
   __syncthreads();
   if (warp == 0) {
     const float p = final_stage(sh, T, st->sse, lane);
     if (lane == 0) st->last_p = st->lstm_override >= 0.0f ? st->lstm_override : p;
   }
   __syncthreads();
-  for (int k = tid; k < N_INPUTS; k += MIX_THREADS) st->x[k] = sh.x[k];
   if (tid < N_L0) st->extras0[tid] = sh.x[N_INPUTS + tid];
   if (tid < N_L1) st->extras1[tid] = sh.l1extra[tid];
   if (tid < L2_IN) st->in2[tid] = sh.in2[tid];
   if (tid < N_MIXERS) st->mix_p[tid] = sh.mixp[tid];
 }
 
+// mix_perceive_kernel<<<26 + 2, 512>>>: Mixer::Perceive (mixer.cpp:56-72) for every mixer and
+// SSE::Perceive (sse.cpp:291-305). CTA i < 26 owns layer-0 mixer i's row; CTA 26 the 21 small rows of
+// layers 1-2, the SSE update and the step counter; CTA 27 the LSTM read-out's bit update
+// (ByteModel::Perceive, byte-model.cpp:17-30).
 __global__ void __launch_bounds__(MIX_THREADS, 1)
 mix_perceive_kernel(StreamState* st, int bit, float decay_base) {
-  __shared__ float upd[N_MIXERS + 1];
-  __shared__ u32 shrink[N_MIXERS + 1];
-  const int tid = threadIdx.x;
-  if (tid < N_MIXERS) upd[tid] = mixer_update_coeff(st->mixer[tid], st->slot[tid], decay_base, st->mix_p[tid], bit, &shrink[tid]);
-  if (tid == 64) sse_perceive(st->sse, bit);
-  __syncthreads();
-  for (int i = 0; i < N_L0; ++i) {
+  __shared__ float upd[N_L1 + 2];
+  __shared__ u32 shrink[N_L1 + 2];
+  const int tid = threadIdx.x, blk = blockIdx.x;
+  if (blk < N_L0) {
+    const int i = blk;
+    if (tid == 0) upd[0] = mixer_update_coeff(st->mixer[i], st->slot[i], decay_base, st->mix_p[i], bit, &shrink[0]);
+    __syncthreads();
     float* row = st->mixer[i].rows + (size_t)st->slot[i] * ROW_PITCH_L0;
     const int n = N_INPUTS + i;
+    const float u = upd[0];
+    const bool shr = shrink[0] != 0;
     for (int k = tid; k < n; k += MIX_THREADS) {
       const float xin = k < N_INPUTS ? st->x[k] : st->extras0[k - N_INPUTS];
-      float w = XM_FSUB(row[k], XM_FMUL(upd[i], xin));
-      if (shrink[i]) w = XM_FMUL(w, 1.0f - 3.0e-6f);
+      float w = XM_FSUB(row[k], XM_FMUL(u, xin));
+      if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
       row[k] = w;
     }
+    return;
   }
+  if (blk == N_L0 + 1) {
+    if (tid == 0) bm_perceive(st->lstm.bm, bit);
+    return;
+  }
+  if (tid < N_L1 + 1) upd[tid] = mixer_update_coeff(st->mixer[N_L0 + tid], st->slot[N_L0 + tid], decay_base, st->mix_p[N_L0 + tid], bit, &shrink[tid]);
+  if (tid == 64) sse_perceive(st->sse, bit);
+  __syncthreads();
   for (int k = tid; k < (N_L1 + 1) * ROW_PITCH_L1; k += MIX_THREADS) {
     const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
     const int mi = N_L0 + i;
@@ -491,8 +539,8 @@ mix_perceive_kernel(StreamState* st, int bit, float decay_base) {
         else xin = st->extras1[c - L1_IN];
       } else xin = st->in2[c];
       float* w = st->mixer[mi].rows + (size_t)st->slot[mi] * ROW_PITCH_L1 + c;
-      float v = XM_FSUB(*w, XM_FMUL(upd[mi], xin));
-      if (shrink[mi]) v = XM_FMUL(v, 1.0f - 3.0e-6f);
+      float v = XM_FSUB(*w, XM_FMUL(upd[i], xin));
+      if (shrink[i]) v = XM_FMUL(v, 1.0f - 3.0e-6f);
       *w = v;
     }
   }

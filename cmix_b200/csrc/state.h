@@ -140,6 +140,7 @@ struct StreamState {
   float x[N_INPUTS + 2];
   float extras0[N_L0 + 2], extras1[N_L1], in2[L2_IN + 3];
   float mix_p[N_MIXERS + 1];
+  float mains[N_L0 + 2];        // layer-0 main dot products (lock-step: row kernel -> final kernel)
   u32 slot[N_MIXERS + 1];
   u32 sel[SEL_PITCH];
   float small_x[SMALL_X_PITCH];

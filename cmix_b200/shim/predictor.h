@@ -29,7 +29,12 @@ class Predictor {
  private:
   Predictor(const Predictor&);
   Predictor& operator=(const Predictor&);
+  void FlushPretrain();
   cmixb200_predictor* impl_;
+  // Pretrain() arrives bit by bit (preprocessor.cpp:52,66) but only before the first Predict():
+  // whole bytes are buffered and trained through the bulk entry point, one launch set per 64 KiB.
+  std::vector<unsigned char> pre_bytes_;
+  unsigned pre_acc_, pre_nbits_;
 };
 
 #endif

@@ -247,3 +247,26 @@ def test_reference_cli_round_trip(tmp_path):
     subprocess.run([cli, "-d", str(arc), str(back)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
     assert back.read_bytes() == data
     assert arc.stat().st_size < len(data)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "build", "cmix_b200_cli")),
+                    reason="reference CLI + shim not built (make -C cmix_b200/shim)")
+def test_reference_cli_round_trip_with_dictionary(tmp_path):
+    """`cmix -c <dictionary> in out`: the reference's WRT preprocessor rewrites the text and calls
+    Pretrain(bit) over the dictionary (preprocessor.cpp:37-69) before the first Predict(); the shim
+    buffers those bits and trains through cmixb200_pretrain_bytes."""
+    import re
+    from collections import Counter
+    from gen_synth import synth_text
+    cli = os.path.join(ROOT, "build", "cmix_b200_cli")
+    data = synth_text(900, 0xE9E80006)
+    words = [w for w, _ in Counter(re.findall(rb"[a-z]{3,}", data)).most_common(150)]
+    dic = tmp_path / "tiny.dic"
+    dic.write_bytes(b"\n".join(words) + b"\n")
+    src = tmp_path / "in.txt"
+    src.write_bytes(data)
+    arc, back = tmp_path / "out.cmix", tmp_path / "back.txt"
+    subprocess.run([cli, "-c", str(dic), str(src), str(arc)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    subprocess.run([cli, "-d", str(dic), str(arc), str(back)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    assert back.read_bytes() == data
+    assert arc.stat().st_size < len(data)
