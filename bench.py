@@ -289,6 +289,21 @@ def main():
     if not all(bool(torch.isfinite(o).all()) and float(o.min()) >= 0.0 and float(o.max()) <= 1.0 for o in h_out):
         raise SystemExit("bench.py: end-to-end probabilities out of range")
 
+    # ---- the decoder's order: Predict()/Perceive(bit) one bit at a time on one stream (not part of `value`) ----
+    lock = None
+    if rank == 0:
+        P0 = streams[0]["P"]
+        n_lock = 128
+        bits = np.unpackbits(streams[0]["text"][:n_lock // 8])
+        for b in bits[:16]:
+            P0.Predict(); P0.Perceive(int(b))
+        t0 = time.perf_counter()
+        for b in bits[16:]:
+            P0.Predict(); P0.Perceive(int(b))
+        P0.Predict()                                     # drains the last queued Perceive()
+        lock = {"us_per_bit": (time.perf_counter() - t0) / (n_lock - 16) * 1e6, "bits": n_lock - 16,
+                "note": "cmixb200_predict/perceive through ctypes, replay inputs at 0.5, host clock"}
+
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         # Launch groups run the same kernel concurrently (engine.cu RunPipelined): n_groups launches overlap, so the
@@ -316,6 +331,7 @@ def main():
                          "concurrent_launches": n_groups, "achieved_per_launch": per_launch,
                          "note": "serial-dependency bound: each dot product is one fp32 FADD chain (bit-exact parity)"},
             "bits_per_s": total_bytes * 8 / dt,
+            "lockstep": lock,
         }
         if (world == 1):
             try:

@@ -66,10 +66,11 @@ struct LstmShared {
   unsigned hist[LH];                         // Lstm::input_history_
   int bmap[256]; unsigned char vocab[256];
   float probs256[256];                       // byte-indexed distribution for the bit read-outs
-  float in[2 * 256 + 2 * LC + 8];   // current layer input vector
+  alignas(16) float in[2 * 256 + 2 * LC + 8];   // current layer input vector
   float gat[3][LC];                  // all-gathered per-gate vector (pre-activations / scaled errors)
-  float gat2[3][LC];                 // all-gathered final gate errors
-  float hid[LSTM_HID + 3];           // full hidden vector (all-gathered)
+  alignas(16) float gat2[3][LC];     // all-gathered final gate errors
+  alignas(16) float prod[3][LC];     // element-wise products feeding the serial RMS-norm sums
+  alignas(16) float hid[LSTM_HID + 3];   // full hidden vector (all-gathered)
   float act[3][LCPC];                // own cells: gate activations
   float eown[3][LCPC];               // own cells: gate errors
   float nown[3][LCPC];               // own cells: norm values of the step
@@ -80,12 +81,46 @@ struct LstmShared {
   alignas(16) float pool[LSTM_POOL_FLOATS];
 };
 
+static_assert(sizeof(LstmShared) <= 232448, "LstmShared must fit the 227 KB of shared memory a CTA can opt into");
+
 #define L_PROF(slot) do { if (prof) { unsigned d_ = *reinterpret_cast<volatile unsigned*>(&sh.sym[0]), k_; \
     asm volatile("mov.u32 %0, %1;" : "=r"(k_) : "r"(d_)); const long long n_ = clock64(); prof[32 + (slot)] += (unsigned long long)(n_ - *tprev) + (k_ & 0u); *tprev = n_; } } while (0)
 
 __device__ __noinline__ float lt_tanhf(float x) { return xm_tanhf(x); }
 __device__ __noinline__ float lt_logistic(float x) { return xm_logistic(x); }
 __device__ __noinline__ float lt_expf(float x) { return xm_expf(x); }
+
+// s = p[n-1] + p[n-2] + ... + p[0], one FADD chain (libstdc++ _Expr::sum() order); n % 4 == 0, p 16-byte aligned
+__device__ __forceinline__ float sum_back_to_front(const float* p, int n) {
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  float4 v = p4[n / 4 - 1];
+  float s = v.w;
+  s = XM_FADD(s, v.z); s = XM_FADD(s, v.y); s = XM_FADD(s, v.x);
+#pragma unroll 4
+  for (int q = n / 4 - 2; q >= 0; --q) {
+    v = p4[q];
+    s = XM_FADD(s, v.w); s = XM_FADD(s, v.z); s = XM_FADD(s, v.y); s = XM_FADD(s, v.x);
+  }
+  return s;
+}
+
+// f += sum_j a[j] * w[j * stride], j = 0..n-1 in order: one FADD chain; the products come two at a time (FMUL2),
+// the broadcast operand as LDS.128. a must be 16-byte aligned.
+__device__ __forceinline__ float chain_strided(float f, const float* a, const float* w, int n, int stride) {
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const int n4 = n >> 2;
+#pragma unroll 4
+  for (int q = 0; q < n4; ++q) {
+    const float4 v = a4[q];
+    const float* wq = w + (size_t)(4 * q) * stride;
+    float p0, p1, p2, p3;
+    xm_fmul2(v.x, v.y, wq[0], wq[stride], p0, p1);
+    xm_fmul2(v.z, v.w, wq[2 * stride], wq[3 * stride], p2, p3);
+    f = XM_FADD(f, p0); f = XM_FADD(f, p1); f = XM_FADD(f, p2); f = XM_FADD(f, p3);
+  }
+  for (int j = 4 * n4; j < n; ++j) f = XM_FADD(f, XM_FMUL(a[j], w[(size_t)j * stride]));
+  return f;
+}
 
 __device__ __forceinline__ float clipf(float v, float c) { return v < -c ? -c : (v > c ? c : v); }
 
@@ -139,9 +174,7 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31;
     const float* w = sh.pool + (size_t)g * gstride + i;
-    f = w[(size_t)in_sizep * LCPC];
-#pragma unroll 8
-    for (int j = 0; j < in_size; ++j) f = XM_FADD(f, XM_FMUL(sh.in[j], w[(size_t)j * LCPC]));
+    f = chain_strided(w[(size_t)in_sizep * LCPC], sh.in, w, in_size, LCPC);
 #pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) {
       float (*rd)[LC] = cluster.map_shared_rank(sh.gat, c);
@@ -151,12 +184,13 @@ __device__ void lstm_layer_forward(cgl::cluster_group& cluster, LstmState& S, in
   L_PROF(5);
   cluster.sync();
   L_PROF(7);
-  // ---- RMS norm: every CTA computes the three sums redundantly (back to front, _Expr::sum()) ----
+  // ---- RMS norm: every CTA computes the three sums redundantly (back to front, _Expr::sum()):
+  //      squares in parallel, then one FADD chain per gate ----
+  for (int k = tid; k < 3 * LC; k += LSTM_THREADS) { const float v = sh.gat[k / LC][k % LC]; sh.prod[k / LC][k % LC] = XM_FMUL(v, v); }
+  __syncthreads();
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
-    float ss = XM_FMUL(sh.gat[g][LC - 1], sh.gat[g][LC - 1]);
-#pragma unroll 8
-    for (int i = LC - 2; i >= 0; --i) ss = XM_FADD(ss, XM_FMUL(sh.gat[g][i], sh.gat[g][i]));
+    const float ss = sum_back_to_front(sh.prod[g], LC);
     const float iv = XM_FDIV(1.0f, __fsqrt_rn(XM_FADD(XM_FDIV(ss, (float)LC), 1e-5f)));
     sh.scal[g] = iv;
     if (rank == 0) P.ivar[l][g][e] = iv;
@@ -227,9 +261,7 @@ __device__ void lstm_predict(cgl::cluster_group& cluster, LstmState& S, unsigned
   __syncthreads();
   if (tid < nrow) {
     const float* wr = sh.pool + (size_t)tid * HW;
-    float sum = 0.0f;
-#pragma unroll 8
-    for (int j = 0; j < HW; ++j) sum = XM_FADD(sum, XM_FMUL(sh.hid[j], wr[j]));
+    const float sum = chain_strided(0.0f, sh.hid, wr, HW, 1);
 #pragma unroll 1
     for (int c = 0; c < LSTM_CTAS; ++c) { float* rl = cluster.map_shared_rank(sh.logits, c); rl[r0 + tid] = sum; }
   }
@@ -307,18 +339,19 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
       rd[g][cell] = escaled;
     }
   }
-  // the full norm vector of this step (for the sum) straight from HBM/L2 into shared memory
-  for (int k = tid; k < 3 * LC; k += LSTM_THREADS) sh.gat2[k / LC][k % LC] = P.norm[l][k / LC][(size_t)ep * LC + (k % LC)];
+  // the full norm vector of this step straight from HBM/L2 into registers while the all-gather lands
+  float nv[2] = {0.0f, 0.0f};
+  for (int k = tid, q = 0; k < 3 * LC; k += LSTM_THREADS, ++q) nv[q] = P.norm[l][k / LC][(size_t)ep * LC + (k % LC)];
   cluster.sync();
+  for (int k = tid, q = 0; k < 3 * LC; k += LSTM_THREADS, ++q) sh.prod[k / LC][k % LC] = XM_FMUL(sh.gat[k / LC][k % LC], nv[q]);
+  __syncthreads();
   if (tid < 96 && (tid & 31) == 0) {
     const int g = tid >> 5;
-    float s = XM_FMUL(sh.gat[g][LC - 1], sh.gat2[g][LC - 1]);
-#pragma unroll 8
-    for (int i = LC - 2; i >= 0; --i) s = XM_FADD(s, XM_FMUL(sh.gat[g][i], sh.gat2[g][i]));
-    sh.scal[g] = XM_FDIV(s, (float)LC);
+    sh.scal[g] = XM_FDIV(sum_back_to_front(sh.prod[g], LC), (float)LC);
   }
   __syncthreads();
-  cluster.sync();                       // everyone finished reading gat/gat2 before they are overwritten
+  // no second cluster barrier: the sums read gat/prod only, and gat2 (written next, remotely) is not read again
+  // before the barrier below; gat itself is next overwritten after that barrier.
   if (tid < 96 && (tid & 31) < LCPC) {
     const int g = tid >> 5, i = tid & 31, cell = LCPC * rank + i;
     const float e = XM_FSUB(escaled, XM_FMUL(sh.scal[g], sh.nown[g][i]));
@@ -338,9 +371,7 @@ __device__ void lstm_layer_backward(cgl::cluster_group& cluster, LstmState& S, i
     if (need) {
       const int ntypes = l + 1;
       const float* w = rec + ((size_t)(g * ntypes + type) * LC) * LCPC + i;
-      float f = 0.0f;
-#pragma unroll 8
-      for (int j = 0; j < LC; ++j) f = XM_FADD(f, XM_FMUL(sh.gat2[g][j], w[(size_t)j * LCPC]));
+      const float f = chain_strided(0.0f, sh.gat2[g], w, LC, LCPC);
       sh.pool[LSTM_POOL_FLOATS - 256 + wv * 32 + i] = f;
     } else {
       sh.pool[LSTM_POOL_FLOATS - 256 + wv * 32 + i] = 0.0f;

@@ -66,22 +66,12 @@ enum { V3_CHUNKS = 8, V3_CHUNK4 = 64 };          // 8 chunks of 64 float4; the l
 
 // One chunk (64 float4) of the serial dot product; the SGD step is applied by the movers chunk by
 // chunk just ahead of this warp. Ping-pong register buffers keep 8 LDS.128 in flight under the FADD chain.
-// Two IEEE fp32 products in one issue slot (FMUL2 on sm_100a): same round-to-nearest result per lane as
-// two scalar FMULs, so the serial FADD chain below still reproduces mixer.cpp:41 bit for bit.
-__device__ __forceinline__ void fmul2(float ax, float ay, float bx, float by, float& px, float& py) {
-  unsigned long long a, b, r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(ax), "f"(ay));
-  asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(bx), "f"(by));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(px), "=f"(py) : "l"(r));
-}
-
 __device__ __forceinline__ float chain_chunk(const float4* __restrict__ x4, const float4* __restrict__ w4, int k0, int k1, float p) {
   float4 xa[4], wa[4], xb[4], wb[4];
 #define CC_LOAD(X, W, k) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { X[q] = x4[(k) + q]; W[q] = w4[(k) + q]; } }
 #define CC_EAT(X, W) { _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
     float p0_, p1_, p2_, p3_; \
-    fmul2(X[q].x, X[q].y, W[q].x, W[q].y, p0_, p1_); fmul2(X[q].z, X[q].w, W[q].z, W[q].w, p2_, p3_); \
+    xm_fmul2(X[q].x, X[q].y, W[q].x, W[q].y, p0_, p1_); xm_fmul2(X[q].z, X[q].w, W[q].z, W[q].w, p2_, p3_); \
     p = XM_FADD(p, p0_); p = XM_FADD(p, p1_); p = XM_FADD(p, p2_); p = XM_FADD(p, p3_); } }
   CC_LOAD(xa, wa, k0);
 #pragma unroll 1
