@@ -525,9 +525,22 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   cmixb200_predictor* lead = preds[0];
   CK(cudaSetDevice(lead->device));
   static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 128;
-  const size_t n_sub = pretrain ? 1 : (n_bytes + kSub - 1) / kSub;
+  // Sub-chunk plan: full sub-chunks, then a geometric tail (64, 32, 16, 16 for a 128-byte remainder). The call
+  // returns when the mixer of the LAST sub-chunk is done, and while it runs the producers have nothing left to
+  // do (two thirds of the SMs idle), so the last sub-chunk is kept short.
+  std::vector<std::pair<size_t, size_t>> subs;
+  if (pretrain) subs.push_back({0, n_bytes});
+  else {
+    size_t off = 0;
+    while (n_bytes - off > kSub) { subs.push_back({off, kSub}); off += kSub; }
+    size_t rem = n_bytes - off;
+    while (rem > 16) { const size_t h = (rem + 1) / 2; subs.push_back({off, h}); off += h; rem -= h; }
+    if (rem) subs.push_back({off, rem});
+  }
+  const size_t n_sub = subs.size();
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
+  u64 decay_steps0 = 0;
   bool any_coder = false;
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
@@ -536,12 +549,13 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
     CK(cudaStreamSynchronize(P->s_small));
     TRY(EnsureScratch(P, n_bytes));
     if (!pretrain) {
-      FillDecay(decay, P->bits_done, n_bytes * 8);
+      // the decay schedule depends only on the number of coded bits: streams that advance together share it
+      // (393 216 double pow() calls per 2 KiB step and stream would otherwise cost more host time than a launch set)
+      if (decay.empty() || decay_steps0 != P->bits_done) { FillDecay(decay, P->bits_done, n_bytes * 8); decay_steps0 = P->bits_done; }
       CK(cudaMemcpy(P->d_decay, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
     }
     for (size_t k = 0; k < n_sub; ++k) {
-      const size_t off = pretrain ? 0 : k * kSub;
-      const size_t n = pretrain ? n_bytes : (n_bytes - off < kSub ? n_bytes - off : kSub);
+      const size_t off = subs[k].first, n = subs[k].second;
       ChunkArgs& a = args[k * n_streams + s];
       memset(&a, 0, sizeof a);
       a.st = P->d_st; a.bytes = d_bytes[s] + off;
