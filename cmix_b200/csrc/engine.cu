@@ -525,13 +525,18 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   cmixb200_predictor* lead = preds[0];
   CK(cudaSetDevice(lead->device));
   static const size_t kSub = getenv("CMIXB200_SUBCHUNK") ? (size_t)atol(getenv("CMIXB200_SUBCHUNK")) : 128;
-  // Sub-chunk plan: full sub-chunks, then a geometric tail (64, 32, 16, 16 for a 128-byte remainder). The call
-  // returns when the mixer of the LAST sub-chunk is done, and while it runs the producers have nothing left to
-  // do (two thirds of the SMs idle), so the last sub-chunk is kept short.
+  // Sub-chunk plan: a geometric head (16, 16, 32, 64), full sub-chunks, a geometric tail (64, 32, 16, 16).
+  // Head: the mixer of a stream cannot start before the producers of its first sub-chunk are done, so the first one
+  // is short. Tail: the call returns when the mixer of the LAST sub-chunk is done, and while it runs the producers
+  // have nothing left to do (two thirds of the SMs idle), so the last one is short too.
   std::vector<std::pair<size_t, size_t>> subs;
   if (pretrain) subs.push_back({0, n_bytes});
   else {
     size_t off = 0;
+    for (size_t h = 16; h < kSub && n_bytes - off > 2 * kSub; h *= 2) {
+      if (h == 16) { subs.push_back({off, h}); off += h; }
+      subs.push_back({off, h}); off += h;
+    }
     while (n_bytes - off > kSub) { subs.push_back({off, kSub}); off += kSub; }
     size_t rem = n_bytes - off;
     while (rem > 16) { const size_t h = (rem + 1) / 2; subs.push_back({off, h}); off += h; rem -= h; }
@@ -782,7 +787,8 @@ int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t
   if (n_streams <= 0 || !preds || !bytes || !p_out) { g_last_error = "code_batch: bad arguments"; return CMIXB200_ERR_ARG; }
   cmixb200_predictor* lead = preds[0];
   CK(cudaSetDevice(lead->device));
-  const size_t kSub = 512;      // staging granularity per stream: 512 B of input = 16.6 MB of replayed codes
+  const size_t kSub = 1024;     // staging granularity per stream: 1024 B of input = 33 MB of replayed codes; long enough
+                                // that a sub-step is bound by SM throughput, not by one stream's serial mixer chain
   if (!lead->s_copy) CK(cudaStreamCreateWithFlags(&lead->s_copy, cudaStreamNonBlocking));
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];

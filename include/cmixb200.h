@@ -63,7 +63,7 @@ int cmixb200_code_bytes_device(cmixb200_predictor*, const uint8_t* d_bytes, size
 int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes,
                                size_t n_bytes, const uint16_t* const* d_ext, const float* const* d_ppmd,
                                float* const* d_p_out);
-/* The batch entry point with HOST buffers: inputs are staged to the device in 512-byte sub-steps on a
+/* The batch entry point with HOST buffers: inputs are staged to the device in 1024-byte sub-steps on a
  * copy stream, double buffered, so the transfer of sub-step k+1 overlaps the kernels of sub-step k; the
  * probabilities return to p_out[s] the same way. All predictors must live on one device. */
 int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t* const* bytes, size_t n_bytes,

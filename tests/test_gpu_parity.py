@@ -153,7 +153,7 @@ def test_batch_of_streams_equals_individual_runs(cm):
 
 
 def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
-    """cmixb200_code_batch: host buffers, 512-byte double-buffered staging; 1100 bytes per stream cross it twice."""
+    """cmixb200_code_batch: host buffers, 1024-byte double-buffered staging; 1100 bytes per stream cross it."""
     from cmix_b200.capi import code_batch
     n = 1100
     runs = [synthetic_streams(n, seed=s) for s in (31, 32)]
