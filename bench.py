@@ -306,13 +306,15 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
-        # Launch groups run the same kernel concurrently (engine.cu RunPipelined): n_groups launches overlap, so the
-        # GPU-level figure is the per-launch bandwidth summed over the launches that are in flight together.
+        # Launch groups run the same kernel concurrently (engine.cu RunPipelined), so the GPU-level figure is the
+        # per-launch bandwidth times the MEASURED mean number of launches in flight = sum of launch durations / wall
+        # time of the timed region (never more than the number of groups).
         group = int(os.environ.get("CMIXB200_GROUP", "8")) or S
         n_groups = (S + group - 1) // group
         bits_per_launch = (S * B * K * 8) / max(mix_n, 1)
         per_launch = ALGO_BYTES_PER_BIT * bits_per_launch / (mix_ms / max(mix_n, 1) / 1e3) / 1e9 if mix_ms > 0 else None
-        achieved = per_launch * n_groups if per_launch else None
+        in_flight = min(float(n_groups), mix_ms / (dt * 1e3)) if mix_ms > 0 else None
+        achieved = per_launch * in_flight if per_launch else None
         out = {
             "metric": "input_MB_per_s", "value": value, "unit": "MB/s", "n_gpus": world if world > 1 else args.gpus,
             "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -328,7 +330,7 @@ def main():
                          "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 4096 bits",
                          "kernel": "mix_kernel_v3", "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
                          "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
-                         "concurrent_launches": n_groups, "achieved_per_launch": per_launch,
+                         "launch_groups": n_groups, "mean_launches_in_flight": in_flight, "achieved_per_launch": per_launch,
                          "note": "serial-dependency bound: each dot product is one fp32 FADD chain (bit-exact parity)"},
             "bits_per_s": total_bytes * 8 / dt,
             "lockstep": lock,
