@@ -145,13 +145,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "24")), help="independent files per GPU")
     ap.add_argument("--step-bytes", type=int, default=2048)
+    ap.add_argument("--ppmd", default=os.environ.get("CMIXB200_BENCH_PPMD", "resident"), choices=["resident", "replay"],
+                    help="PPMD byte model: resident on the device (ppmd.cuh) or a synthetic replayed distribution")
     ap.add_argument("--cpu-sample-bytes", type=int, default=4096)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "configs[1]: synthetic enwik8-shaped ASCII text, full mixer + LSTM + small models; "
-                          "PAQ8/FXCM/PPMD outputs as synthetic replay streams",
+                          "PAQ8/FXCM outputs as synthetic replay streams; PPMD %s" % ("resident on the device" if args.ppmd == "resident" else "replayed"),
               "streams_per_gpu": args.streams, "step_bytes_per_stream": args.step_bytes,
               "parallelism": "independent streams sharded over %d rank(s), no data-path collective" % max(world, args.gpus),
               "l2": "inputs larger than L2: every step streams %.0f MB of fresh replay codes per stream and walks ~6 GB of "
@@ -214,7 +216,8 @@ def main():
     def run_step(i):
         lo, hi = i * B, (i + 1) * B
         code_batch_device([st["P"] for st in streams], [st["d_bytes"][lo:hi] for st in streams], B,
-                          [st["d_ext"][lo * 8:hi * 8] for st in streams], [st["d_ppmd"][lo:hi] for st in streams],
+                          [st["d_ext"][lo * 8:hi * 8] for st in streams],
+                          [st["d_ppmd"][lo:hi] for st in streams] if args.ppmd == "replay" else None,
                           [st["d_out"][lo * 8:hi * 8] for st in streams])
 
     for i in range(W):
@@ -266,7 +269,7 @@ def main():
 
     def e2e_step(j):
         code_batch(preds, [t[j * B:] for t in h_bytes], B, [t[j * B * 8 * N_EXT:] for t in h_ext],
-                   [t[j * B * 256:] for t in h_ppmd], [t[j * B * 8:] for t in h_out])
+                   [t[j * B * 256:] for t in h_ppmd] if args.ppmd == "replay" else None, [t[j * B * 8:] for t in h_out])
 
     h_ext = [t.view(-1) for t in h_ext]
     h_ppmd = [t.view(-1) for t in h_ppmd]
@@ -284,7 +287,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt_e2e = float(tt.item())
     e2e_value = S * n_e2e * B * world / dt_e2e / 1e6
-    h2d = S * (B + B * 8 * N_EXT * 2 + B * 256 * 4 + B * 8 * 4)   # per rank: bytes + codes + PPMD + decay table
+    h2d = S * (B + B * 8 * N_EXT * 2 + (B * 256 * 4 if args.ppmd == "replay" else 0) + B * 8 * 4)   # per rank: bytes + codes (+ PPMD) + decay table
     d2h = S * B * 8 * 4
     if not all(bool(torch.isfinite(o).all()) and float(o.min()) >= 0.0 and float(o.max()) <= 1.0 for o in h_out):
         raise SystemExit("bench.py: end-to-end probabilities out of range")

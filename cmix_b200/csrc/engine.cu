@@ -29,6 +29,7 @@
 #include "lstm.cuh"
 #include "mixer.cuh"
 #include "mixer_v3.cuh"
+#include "ppmd.cuh"
 #include "small_models.cuh"
 #include "state.h"
 
@@ -244,6 +245,7 @@ int BuildSharedTables(int device) {
   CK(cudaFuncSetAttribute(mix_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared3)));
   CK(cudaFuncSetAttribute(mix_predict_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
+  CK(cudaFuncSetAttribute(ppmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PPMD_WARPS * sizeof(PpmdWarpShared))));
   CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   g_tables.ready = true;
   g_tables.device = device;
@@ -267,6 +269,8 @@ struct cmixb200_predictor {
   u8* d_bytes2[2] = {nullptr, nullptr}; u16* d_ext2[2] = {nullptr, nullptr}; float* d_ppmd2[2] = {nullptr, nullptr};
   size_t stage2_bytes = 0; cudaStream_t s_copy = nullptr;
   // device arithmetic coder (compress direction)
+  cudaStream_t s_ppmd = nullptr; float* d_ppmd_gen = nullptr; size_t ppmd_gen_bytes = 0;   // resident PPMD: own stream, scratch [n_bytes][256]
+  PpmdModel* d_ppmd_model = nullptr;
   cudaEvent_t ev_lock_mix = nullptr, ev_lock_small = nullptr;   // lock-step: order the two library streams per bit
   CoderState* d_coder = nullptr; u8* d_code = nullptr; size_t code_cap = 0; bool coder_on = false;
   // lock-step state
@@ -449,6 +453,23 @@ int BuildStream(cmixb200_predictor* P) {
   h.lstm_override = -1.0f;
   h.last_p = 0.5f;
   TRY(P->Alloc(&P->d_st, 1));
+  // ---------------- PPMD (ppmd_model.h): model registers + three flat arenas ----------------
+  {
+    const char* mb_env = getenv("CMIXB200_PPMD_MB");
+    const size_t mb = mb_env ? (size_t)atol(mb_env) : 32;           // 32 MB: ~0.5 M contexts, roughly 150-500 KB of input
+    PpmdModel pm;
+    memset(&pm, 0, sizeof pm);
+    pm.ctx_cap = (uint32_t)(mb * (1u << 20) / 4 / sizeof(PpmdCtx));
+    pm.pool_cap = (uint32_t)(mb * (1u << 20) / 2 / sizeof(PpmdSt));
+    pm.text_cap = (uint32_t)(mb * (1u << 20) / 4);
+    TRY(P->Alloc(&pm.ctx, pm.ctx_cap, false));
+    TRY(P->Alloc(&pm.pool, pm.pool_cap, false));
+    TRY(P->Alloc(&pm.text, pm.text_cap, false));
+    TRY(P->Alloc(&P->d_ppmd_model, 1, false));
+    CK(cudaMemcpy(P->d_ppmd_model, &pm, sizeof pm, cudaMemcpyHostToDevice));
+    ppmd_init_kernel<<<1, 32>>>(P->d_ppmd_model);
+    h.ppmd = P->d_ppmd_model;
+  }
   CK(cudaMemcpy(P->d_st, &h, sizeof h, cudaMemcpyHostToDevice));
   CK(cudaDeviceSynchronize());
   return CMIXB200_OK;
@@ -486,8 +507,20 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 }
 
 // Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
-int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false) {
+int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false,
+                bool with_ppmd = false) {
   const Tables T = g_tables.T;
+  if (with_ppmd && !pretrain) {
+    // the PPMD producer runs ahead on its own stream; both consumers of its distributions wait for this sub-chunk's
+    ppmd_kernel<<<(n_streams + PPMD_WARPS - 1) / PPMD_WARPS, PPMD_WARPS * 32, PPMD_WARPS * sizeof(PpmdWarpShared), lead->s_ppmd>>>(d_args, n_streams);
+    lead->launches++;
+    cudaEvent_t e0;
+    CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    CK(cudaEventRecord(e0, lead->s_ppmd));
+    CK(cudaStreamWaitEvent(lead->s_small, e0, 0));
+    CK(cudaStreamWaitEvent(lead->s_lstm, e0, 0));
+    CK(cudaEventDestroy(e0));
+  }
   small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
   lead->launches++;
   if (!pretrain) {
@@ -546,13 +579,19 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
   u64 decay_steps0 = 0;
-  bool any_coder = false;
+  bool any_coder = false, any_ppmd = false;
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
     if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
     CK(cudaStreamSynchronize(P->s_mix));                 // a lock-step Perceive() may still be in flight
     CK(cudaStreamSynchronize(P->s_small));
     TRY(EnsureScratch(P, n_bytes));
+    if (!pretrain && !(d_ppmd && d_ppmd[s]) && P->ppmd_gen_bytes < n_bytes) {
+      if (P->d_ppmd_gen) cudaFree(P->d_ppmd_gen);
+      P->d_ppmd_gen = nullptr; P->ppmd_gen_bytes = 0;
+      CK(cudaMalloc(&P->d_ppmd_gen, n_bytes * 256 * sizeof(float)));
+      P->ppmd_gen_bytes = n_bytes;
+    }
     if (!pretrain) {
       // the decay schedule depends only on the number of coded bits: streams that advance together share it
       // (393 216 double pow() calls per 2 KiB step and stream would otherwise cost more host time than a launch set)
@@ -566,6 +605,11 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
       a.st = P->d_st; a.bytes = d_bytes[s] + off;
       a.ext = (d_ext && d_ext[s]) ? d_ext[s] + off * 8 * N_EXT : nullptr;
       a.ppmd = (d_ppmd && d_ppmd[s]) ? d_ppmd[s] + off * 256 : nullptr;
+      if (!a.ppmd && !pretrain) {                                   // no replay: the resident model produces the distributions
+        a.ppmd_gen = P->d_ppmd_gen + off * 256;
+        a.ppmd = a.ppmd_gen;
+        any_ppmd = true;
+      }
       a.decay = P->d_decay + off * 8;
       a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
       a.lstm_x = P->d_lstm_x + off * 8 * 2;
@@ -592,18 +636,26 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   for (size_t k = 0; k < n_sub; ++k)
     for (int g0 = 0; g0 < n_streams; g0 += gsz) {
       const int cnt = n_streams - g0 < gsz ? n_streams - g0 : gsz;
-      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder));
+      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder, any_ppmd));
     }
   for (int g0 = 0; g0 < n_streams; g0 += gsz) {
     cmixb200_predictor* G = preds[g0];
     CK(cudaStreamSynchronize(G->s_small));
     if (!pretrain) {
+      if (any_ppmd) CK(cudaStreamSynchronize(G->s_ppmd));
       CK(cudaStreamSynchronize(G->s_lstm));
       CK(cudaStreamSynchronize(G->s_mix));
     }
     HarvestMixTimes(G);
   }
   if (!pretrain) for (int s = 0; s < n_streams; ++s) preds[s]->bits_done += n_bytes * 8;
+  if (any_ppmd) {
+    for (int s = 0; s < n_streams; ++s) {
+      uint32_t err = 0;
+      CK(cudaMemcpy(&err, (const char*)preds[s]->d_ppmd_model + offsetof(PpmdModel, error), 4, cudaMemcpyDeviceToHost));
+      if (err) { g_last_error = "PPMD arena exhausted: raise CMIXB200_PPMD_MB (the reference would cut its model off here)"; return CMIXB200_ERR_CAPACITY; }
+    }
+  }
   return CMIXB200_OK;
 }
 
@@ -641,6 +693,7 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
     cudaStreamCreateWithPriority(&P->s_small, cudaStreamNonBlocking, p_small);
     cudaStreamCreateWithPriority(&P->s_lstm, cudaStreamNonBlocking, p_lstm);
     cudaStreamCreateWithPriority(&P->s_mix, cudaStreamNonBlocking, p_mix);
+    cudaStreamCreateWithPriority(&P->s_ppmd, cudaStreamNonBlocking, p_mix);      // one warp per stream, must never be the one waited for
     cudaEventCreateWithFlags(&P->ev_lock_mix, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_lock_small, cudaEventDisableTiming);
     cudaEventRecord(P->ev_lock_mix, P->s_mix);
@@ -666,6 +719,8 @@ void cmixb200_destroy(cmixb200_predictor* P) {
   if (P->ev_lock_small) cudaEventDestroy(P->ev_lock_small);
   if (P->d_coder) cudaFree(P->d_coder);
   if (P->d_code) cudaFree(P->d_code);
+  if (P->s_ppmd) cudaStreamDestroy(P->s_ppmd);
+  if (P->d_ppmd_gen) cudaFree(P->d_ppmd_gen);
   if (P->s_copy) cudaStreamDestroy(P->s_copy);
   if (P->s_small) cudaStreamDestroy(P->s_small);
   if (P->s_lstm) cudaStreamDestroy(P->s_lstm);
@@ -711,8 +766,15 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   bit = bit ? 1 : 0;
   const bool byte_done = P->bit_context >= 128;
   const u32 full = (P->bit_context * 2 + bit) & 255;
-  const float* ppmd = (byte_done && P->ppmd_byte_valid) ? P->d_ppmd_byte : nullptr;
+  const float* ppmd = byte_done ? P->d_ppmd_byte : nullptr;
   float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
+  if (byte_done && !P->ppmd_byte_valid) {
+    // no replayed distribution for this byte: the resident PPMD model is updated and emits it (ppmd.cpp:1328-1338)
+    ppmd_byte_kernel<<<1, 32, sizeof(PpmdWarpShared), P->s_small>>>(P->d_st, full, P->d_ppmd_byte);
+    P->launches++;
+    CK(cudaEventRecord(P->ev_lock_small, P->s_small));
+    CK(cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0));          // lstm_byte_kernel reads it too
+  }
   // queued, not awaited: the host goes back to the arithmetic coder while the update runs; the next
   // Predict() (same CUDA stream) is ordered behind it
   small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, ppmd, 0);      // concurrent with the mixer / LSTM update
@@ -881,6 +943,10 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
     case CMIXB200_DBG_LSTM_X: src = P->d_lstm_x; break;
     case CMIXB200_DBG_LSTM_PROBS: src = &P->d_st->lstm.bm.probs[0]; break;
     case CMIXB200_DBG_ERROR_FLAGS: src = &P->d_st->small.error; break;
+    case CMIXB200_DBG_PPMD_PROBS: src = P->d_ppmd_byte; break;
+    case CMIXB200_DBG_PPMD_BULK:
+      if (bytes > P->ppmd_gen_bytes * 256 * sizeof(float)) { g_last_error = "debug_fetch: more PPMD rows than the last bulk call produced"; return CMIXB200_ERR_ARG; }
+      src = P->d_ppmd_gen; break;
     case CMIXB200_DBG_PROFILE:
       if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 64 * 8)); CK(cudaMemset(P->d_prof, 0, 64 * 8)); }
       src = P->d_prof; break;

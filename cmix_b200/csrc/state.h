@@ -9,6 +9,8 @@
 
 #include <stdint.h>
 
+#include "ppmd_model.h"
+
 namespace cmixb200 {
 
 typedef uint64_t u64;
@@ -144,6 +146,7 @@ struct StreamState {
   u32 slot[N_MIXERS + 1];
   u32 sel[SEL_PITCH];
   float small_x[SMALL_X_PITCH];
+  PpmdModel* ppmd;              // resident PPMD model (ppmd_model.h); its arenas are separate allocations
   float lstm_x, lstm_override;  // override: -1 none, else 0 or 1 (predictor.cpp:383)
   float last_p;
 };
@@ -168,7 +171,8 @@ struct ChunkArgs {
   StreamState* st;
   const u8* bytes;              // [n_bytes] the coded stream
   const u16* ext;               // [n_bytes*8][N_EXT] or null (all 0.5)
-  const float* ppmd;            // [n_bytes][256] or null (uniform over the vocabulary)
+  const float* ppmd;            // [n_bytes][256] PPMD distribution after each byte: replayed, or == ppmd_gen; null = flat
+  float* ppmd_gen;              // when non-null the resident PPMD model (ppmd.cuh) writes the distributions here
   const float* decay;           // [n_bytes*8] 0.9/pow(1e-7*steps+0.8, 0.8) (mixer.cpp:58), host-built
   float* small_x;               // [n_bytes*8][SMALL_X_PITCH] scratch: small-model inputs (+ PPMD)
   u32* sel;                     // [n_bytes*8][SEL_PITCH]   scratch: mixer selector values

@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-enum { CMIXB200_OK = 0, CMIXB200_ERR_CUDA = 1, CMIXB200_ERR_ARG = 2 };
+enum { CMIXB200_OK = 0, CMIXB200_ERR_CUDA = 1, CMIXB200_ERR_ARG = 2,
+       CMIXB200_ERR_CAPACITY = 3 /* a model arena is full (PPMD: raise CMIXB200_PPMD_MB); the stream is unusable */ };
 
 enum {
   CMIXB200_N_EXT = 2022,  /* replayed FXCM (431) + PAQ8 (1591) outputs per bit, as 12-bit codes k
@@ -91,7 +92,9 @@ void* cmixb200_mix_stream(cmixb200_predictor*);
 /* test hooks: copy intermediate arrays of the last bulk call to the host */
 enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, CMIXB200_DBG_LSTM_PROBS = 4,
        CMIXB200_DBG_ERROR_FLAGS = 5,
-       CMIXB200_DBG_PROFILE = 6 /* 64 u64 per-phase cycle counters; first fetch enables them */ };
+       CMIXB200_DBG_PROFILE = 6 /* 64 u64 per-phase cycle counters; first fetch enables them */,
+       CMIXB200_DBG_PPMD_PROBS = 7 /* 256 f32: the resident PPMD model's distribution after the last lock-step byte */,
+       CMIXB200_DBG_PPMD_BULK = 8 /* [n_bytes][256] f32: the distributions the resident model produced in the last bulk call */ };
 int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
 
 #ifdef __cplusplus

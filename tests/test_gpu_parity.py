@@ -167,6 +167,73 @@ def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
         assert np.abs(o - w).max() <= TOL
 
 
+def test_resident_ppmd_replaces_the_replayed_distribution(cm, golden):
+    """No PPMD replay: the device model (ppmd.cuh) must reproduce the reference's
+    distributions, so every Predict() still equals the reference bit for bit."""
+    g = golden
+    P = cm.Predictor(g.vocab)
+    k = 37                                        # two bulk calls: the model's state carries over
+    p = np.concatenate([P.code_bytes(g.stream[:k], g.ext[:k * 8], None), P.code_bytes(g.stream[k:], g.ext[k * 8:], None)])
+    P.close()
+    assert np.array_equal(p, g.p)
+
+
+def test_resident_ppmd_lock_step(cm, golden_text):
+    g = golden_text
+    bits = g.bits()
+    n = 24
+    P = cm.Predictor(g.vocab)
+    for t in range(n * 8):
+        P.feed_external_bit(g.ext[t])
+        assert P.Predict() == g.p[t], "bit %d" % t
+        P.Perceive(int(bits[t]))                  # no feed_external_byte: the resident model supplies it
+        if t % 8 == 7:
+            assert np.array_equal(P.debug_fetch(7, (256,), np.float32), g.ppmd[t // 8])
+    P.close()
+
+
+@pytest.mark.parametrize("name", ["ppmd_text40k", "ppmd_bin6k"])
+def test_resident_ppmd_distributions_on_device(cm, name):
+    """The device build of ppmd_model.h against fixtures from reference dumps (one CRC per byte)."""
+    import zlib
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    n = min(12000, g["stream"].size)
+    import torch
+    P = cm.Predictor(g["vocab"])
+    d_bytes = torch.from_numpy(g["stream"][:n].copy()).cuda()
+    d_out = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+    P.code_bytes_device(d_bytes, n, None, None, d_out)          # one call: the debug fetch returns the last call's rows
+    torch.cuda.synchronize()
+    rows = P.debug_fetch(8, (n, 256), np.float32)
+    P.close()
+    got = np.array([zlib.crc32(rows[t].tobytes()) for t in range(n)], dtype=np.uint32)
+    bad = np.nonzero(got != g["crc"][:n])[0]
+    assert bad.size == 0, "first differing byte %d" % bad[0]
+
+
+def test_resident_ppmd_in_a_batch(cm):
+    """Several streams share one PPMD CTA (one warp each): same result as running them alone."""
+    import torch
+    from cmix_b200.capi import code_batch_device
+    runs = [synthetic_streams(300, seed=s) for s in (41, 42, 43)]
+    singles = []
+    for stream, vocab, codes, _ in runs:
+        P = cm.Predictor(vocab)
+        singles.append(P.code_bytes(stream, codes, None))
+        P.close()
+    preds = [cm.Predictor(r[1]) for r in runs]
+    dev = torch.device("cuda:0")
+    d_bytes = [torch.from_numpy(r[0]).to(dev) for r in runs]
+    d_ext = [torch.from_numpy(r[2].view(np.int16)).to(dev) for r in runs]
+    d_out = [torch.empty(300 * 8, dtype=torch.float32, device=dev) for _ in runs]
+    code_batch_device(preds, d_bytes, 300, d_ext, None, d_out)
+    torch.cuda.synchronize()
+    for o, s in zip(d_out, singles):
+        assert np.array_equal(o.cpu().numpy(), s)
+    for p in preds:
+        p.close()
+
+
 def test_device_coder_writes_the_reference_archive_bytes(cm, port, golden_text):
     """Encoder::Encode/Flush on the device (coder.cuh): the archive body equals the host coder's over the
     reference's own probabilities, across two bulk calls, and decodes back to the input bits."""
