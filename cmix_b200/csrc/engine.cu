@@ -944,6 +944,7 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
     case CMIXB200_DBG_LSTM_PROBS: src = &P->d_st->lstm.bm.probs[0]; break;
     case CMIXB200_DBG_ERROR_FLAGS: src = &P->d_st->small.error; break;
     case CMIXB200_DBG_PPMD_PROBS: src = P->d_ppmd_byte; break;
+    case CMIXB200_DBG_PPMD_PROFILE: src = (const char*)P->d_ppmd_model + offsetof(PpmdModel, prof); break;
     case CMIXB200_DBG_PPMD_BULK:
       if (bytes > P->ppmd_gen_bytes * 256 * sizeof(float)) { g_last_error = "debug_fetch: more PPMD rows than the last bulk call produced"; return CMIXB200_ERR_ARG; }
       src = P->d_ppmd_gen; break;

@@ -31,6 +31,12 @@
 #else
 #define PP_HD inline
 #endif
+// Per-phase cycle accounting on the device (tools/ppmd_prof.py); compiled out on the host.
+#if defined(__CUDA_ARCH__)
+#define PP_TICK(m, k) do { const long long now_ = clock64(); (m).prof[k] += (unsigned long long)(now_ - (m).tprev); (m).tprev = now_; } while (0)
+#else
+#define PP_TICK(m, k) do { } while (0)
+#endif
 
 namespace cmixb200 {
 
@@ -72,6 +78,8 @@ struct PpmdModel {
   // PrepareByte scratch
   PpmdQ sq[1024]; uint32_t sq_n;
   uint32_t sqp[256];
+  // cycles per phase (device only): 0 symbol search, 1 model update, 2 suffix walk of PrepareByte, 3 ConvertSQ, 4 emit, 5 bytes
+  unsigned long long prof[6]; long long tprev;
 };
 
 PP_HD bool pp_is_ctx(uint32_t v) { return v >= PPMD_CTX_BASE; }
@@ -108,6 +116,8 @@ PP_HD void pp_see_update(PpmdSee& s) {
 PP_HD void ppmd_init(PpmdModel& m) {
   static const signed char kEscCoef[12] = {16, -10, 1, 51, 14, 89, 23, 35, 64, 26, -42, 43};
   m.error = 0;
+  for (int i = 0; i < 6; ++i) m.prof[i] = 0;
+  m.tprev = 0;
   m.ns2bs[0] = 0; m.ns2bs[1] = 2; m.ns2bs[2] = 2;
   for (int i = 3; i < 29; ++i) m.ns2bs[i] = 4;
   for (int i = 29; i < 256; ++i) m.ns2bs[i] = 6;
@@ -525,10 +535,12 @@ PP_HD void ppmd_update_byte(PpmdModel& m, int c) {
     } while (pp_ctx(m, minc).ns == m.num_masked);
     pp_symbol2(m, pp_ctx(m, minc), c);
   }
+  PP_TICK(m, 0);
   uint32_t r;
   if (m.order_fall != 0 || !pp_is_ctx(m.pool[m.found].succ)) r = pp_update_model(m, minc);
   else { r = m.pool[m.found].succ; m.max_context = r; }
   if (!r) m.error = 1;                       // the reference would cut the model off here (RestoreModelRare)
+  PP_TICK(m, 1);
 }
 
 PP_HD void pp_sq_store(PpmdModel& m, uint32_t sym, uint32_t freq, uint32_t total) {
@@ -584,6 +596,7 @@ PP_HD void ppmd_prepare_byte(PpmdModel& m) {
     m.num_masked = cnum;
   }
   m.esc_count++; m.num_masked = 0; m.order_fall = saved_fall;
+  PP_TICK(m, 2);
   uint32_t cum = 0xFFFFFF00u;
   for (int i = 0; i < 256; ++i) m.sqp[i] = 0;
   for (uint32_t i = 0; i < m.sq_n; ++i) {
@@ -591,6 +604,7 @@ PP_HD void ppmd_prepare_byte(PpmdModel& m) {
     const uint32_t prob = (uint32_t)(((uint64_t)cum * freq) / total);
     if (c < 256) m.sqp[c] = prob + 1; else cum = prob;
   }
+  PP_TICK(m, 3);
 }
 
 }  // namespace cmixb200

@@ -94,6 +94,7 @@ enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, 
        CMIXB200_DBG_ERROR_FLAGS = 5,
        CMIXB200_DBG_PROFILE = 6 /* 64 u64 per-phase cycle counters; first fetch enables them */,
        CMIXB200_DBG_PPMD_PROBS = 7 /* 256 f32: the resident PPMD model's distribution after the last lock-step byte */,
+       CMIXB200_DBG_PPMD_PROFILE = 9 /* 6 u64: cycles in symbol search, model update, suffix walk, ConvertSQ, emit; bytes */,
        CMIXB200_DBG_PPMD_BULK = 8 /* [n_bytes][256] f32: the distributions the resident model produced in the last bulk call */ };
 int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
 
