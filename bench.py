@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-NCU_DRAM_BYTES_PER_BIT = 29423      # (92.84 MB read + 27.68 MB written) / 4096 bits, ncu --set full, profiles/r01_*
+NCU_DRAM_BYTES_PER_BIT = 34786      # (63.16 MB read + 8.09 MB written) / 2048 bits of one launch, ncu --set full, profiles/r01_ncu_full_metrics.csv
 ALGO_BYTES_PER_BIT = 450_000          # 55 172 fp32 weights read + written, + input vectors
 N_EXT = 2022
 
@@ -332,7 +332,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": NCU_DRAM_BYTES_PER_BIT * bits_per_launch, "traffic_unit": "B per launch",
-                         "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 4096 bits",
+                         "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 2048 bits",
                          "kernel": "mix_kernel_v3", "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
                          "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
                          "launch_groups": n_groups, "mean_launches_in_flight": in_flight, "achieved_per_launch": per_launch,
