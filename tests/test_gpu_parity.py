@@ -192,7 +192,7 @@ def test_resident_ppmd_lock_step(cm, golden_text):
     P.close()
 
 
-@pytest.mark.parametrize("name", ["ppmd_text40k", "ppmd_bin6k"])
+@pytest.mark.parametrize("name", ["ppmd_text40k", "ppmd_bin6k", "ppmd_rand", "ppmd_rep", "ppmd_dic"])
 def test_resident_ppmd_distributions_on_device(cm, name):
     """The device build of ppmd_model.h against fixtures from reference dumps (one CRC per byte)."""
     import zlib

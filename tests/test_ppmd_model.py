@@ -35,7 +35,7 @@ def ppmd_host(tmp_path_factory):
     return run
 
 
-@pytest.mark.parametrize("name", ["ppmd_text40k", "ppmd_bin6k"])
+@pytest.mark.parametrize("name", ["ppmd_text40k", "ppmd_bin6k", "ppmd_rand", "ppmd_rep", "ppmd_dic"])
 def test_distributions_match_the_reference_dump(ppmd_host, name):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     rc, out = ppmd_host(g["stream"], g["vocab"])
