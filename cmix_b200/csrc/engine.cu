@@ -9,9 +9,9 @@
 //  * draw the initial LSTM weights / Indirect offsets from glibc's rand() stream
 //    seeded with 0xDEADBEEF in the reference's construction order
 //    (predictor.cpp:26-36);
-//  * allocate the ~6 GB of per-stream HBM state and launch the three bulk
-//    kernels (small | lstm | mix) on separate CUDA streams, or their lock-step
-//    halves for Predict()/Perceive().
+//  * allocate the ~7 GB of per-stream HBM state and launch the bulk kernels
+//    (ppmd -> small | lstm -> mix [-> encode]) on separate CUDA streams, in launch
+//    groups of 8 streams, or their lock-step halves for Predict()/Perceive().
 // There is NO CPU fallback: every entry point fails with CMIXB200_ERR_CUDA if
 // the device or a kernel is unavailable.
 #include <cuda_runtime.h>
