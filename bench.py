@@ -202,16 +202,25 @@ def main():
     streams = []
     free0 = torch.cuda.mem_get_info(dev)[0]
     for s in stream_block(S * world, world, rank):      # global stream ids owned by this rank (weak scaling: S per GPU)
+        if len(streams) >= S:
+            break
         text, vocab, d_bytes, d_ext, d_ppmd = make_inputs(torch, dev, B * total_steps, seed=s)
         P = cmix_b200.Predictor(vocab, device=local_rank)
         d_out = torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)
         streams.append(dict(P=P, text=text, d_bytes=d_bytes, d_ext=d_ext, d_ppmd=d_ppmd, d_out=d_out))
         if len(streams) == 1:
-            # every stream owns ~6 GB of model tables: refuse a stream count that cannot fit instead of running the box out of memory
+            # every stream owns ~7 GB of model tables: run as many streams as fit (the same number on every rank)
+            # instead of driving the box out of memory
             per_stream = free0 - torch.cuda.mem_get_info(dev)[0] + 2 * 1024 * (8 * N_EXT * 2 + 256 * 4) + (64 << 20)
-            if per_stream * S > 0.94 * free0:
-                raise SystemExit("bench.py: %d streams x %.1f GB do not fit in %.0f GB of free HBM; lower --streams"
-                                 % (S, per_stream / 1e9, free0 / 1e9))
+            s_fit = max(1, int(0.94 * free0 // per_stream))
+            if dist:
+                t_fit = torch.tensor([s_fit], device=dev, dtype=torch.int64)
+                dist.all_reduce(t_fit, op=dist.ReduceOp.MIN)
+                s_fit = int(t_fit.item())
+            if s_fit < S:
+                config["streams_requested"] = S
+                S = s_fit
+                config["streams_per_gpu"] = S
             config["hbm_per_stream_gb"] = round(per_stream / 1e9, 2)
     torch.cuda.synchronize()
 
