@@ -23,6 +23,8 @@
 //                                    (0xFFFF = slot still holds its initial 0.5)
 //               + <prefix>.ppmd.f32 per byte: the 256-entry PPMD distribution
 //                                    valid AFTER that byte (ppmd.cpp:1328-1338)
+//               + <prefix>.lstmfx.u32 per bit: lstmpr | lstmex << 16 as FXCM saw them in the
+//                                    Perceive() of that bit (predictor.cpp:462-466)
 // dump level 2: + <prefix>.in.f32   per bit: 2078 stretched layer-0 inputs
 //               + <prefix>.mix.f32  per bit: 47 raw mixer outputs (Mixer::p_)
 //               + <prefix>.ctx.u32  per bit: 47 mixer selector contexts (u32)
@@ -88,7 +90,7 @@ uint16_t code12(float p) {
 }
 
 struct Files {
-  FILE *p = 0, *ext = 0, *ppmd = 0, *in = 0, *mix = 0, *ctx = 0, *lstm = 0;
+  FILE *p = 0, *ext = 0, *ppmd = 0, *in = 0, *mix = 0, *ctx = 0, *lstm = 0, *lstmfx = 0;
 };
 
 FILE* open_out(const std::string& prefix, const char* suffix) {
@@ -171,7 +173,7 @@ int main(int argc, char** argv) {
   if (cmd == "dump") {
     Files f;
     f.p = open_out(prefix, ".p.f32");
-    if (level >= 1) { f.ext = open_out(prefix, ".ext.u16"); f.ppmd = open_out(prefix, ".ppmd.f32"); }
+    if (level >= 1) { f.ext = open_out(prefix, ".ext.u16"); f.ppmd = open_out(prefix, ".ppmd.f32"); f.lstmfx = open_out(prefix, ".lstmfx.u32"); }
     if (level >= 2) {
       f.in = open_out(prefix, ".in.f32"); f.mix = open_out(prefix, ".mix.f32");
       f.ctx = open_out(prefix, ".ctx.u32"); f.lstm = open_out(prefix, ".lstm.f32");
@@ -204,6 +206,7 @@ int main(int argc, char** argv) {
           fwrite(ctxv.data(), 4, 47, f.ctx);
         }
         p.Perceive(bit);
+        if (f.lstmfx) { uint32_t v = (uint32_t)lstmpr | ((uint32_t)lstmex << 16); fwrite(&v, 4, 1, f.lstmfx); }
       }
       if (f.ppmd) {
         const std::valarray<float>& pp = p.byte_models_[0]->BytePredict();
@@ -221,7 +224,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 256; ++i) fputc(vocab[i] ? '1' : '0', meta);
     fprintf(meta, "\nctor_s %.3f\npretrain_s %.3f\ncode_s %.3f\n", t_ctor - t_start, t_pretrain - t_ctor, t_end - t_pretrain);
     fclose(meta);
-    for (FILE* x : {f.p, f.ext, f.ppmd, f.in, f.mix, f.ctx, f.lstm}) if (x) fclose(x);
+    for (FILE* x : {f.p, f.ext, f.ppmd, f.in, f.mix, f.ctx, f.lstm, f.lstmfx}) if (x) fclose(x);
     return 0;
   }
 
