@@ -43,6 +43,8 @@ def load_library():
     vp = c.c_void_p
     lib.cmixb200_create.argtypes = [vp, c.c_char_p, c.c_int, c.POINTER(vp)]
     lib.cmixb200_create.restype = c.c_int
+    lib.cmixb200_create_ex.argtypes = [vp, c.c_char_p, c.c_int, c.c_uint, c.POINTER(vp)]
+    lib.cmixb200_create_ex.restype = c.c_int
     lib.cmixb200_destroy.argtypes = [vp]
     lib.cmixb200_destroy.restype = None
     lib.cmixb200_predict.argtypes = [vp]
@@ -89,13 +91,19 @@ def _ptr(a):
 class Predictor:
     """Mirror of the reference `Predictor` (src/predictor.h:17-53) on one B200."""
 
-    def __init__(self, vocab, dictionary_path=None, device=0):
+    REPLAY = {"fxcm": 1, "paq8": 2}
+
+    def __init__(self, vocab, dictionary_path=None, device=0, replay=()):
+        """`replay`: model groups ("fxcm", "paq8") whose outputs are replayed instead of computed on the device."""
         self._lib = load_library()
         v = np.ascontiguousarray(np.asarray(vocab, dtype=np.uint8))
         assert v.size == 256
         h = ctypes.c_void_p()
         d = dictionary_path.encode() if dictionary_path else None
-        _check(self._lib, self._lib.cmixb200_create(v.ctypes.data, d, int(device), ctypes.byref(h)), "create")
+        mask = 0
+        for name in replay:
+            mask |= self.REPLAY[name]
+        _check(self._lib, self._lib.cmixb200_create_ex(v.ctypes.data, d, int(device), mask, ctypes.byref(h)), "create")
         self._h = h
         self.device = device
 

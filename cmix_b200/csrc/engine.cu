@@ -20,12 +20,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/cmixb200.h"
 #include "exact_math.h"
 #include "coder.cuh"
+#include "fxcm.cuh"
+#include "fxcm_host.h"
 #include "lstm.cuh"
 #include "mixer.cuh"
 #include "mixer_v3.cuh"
@@ -147,16 +151,26 @@ __global__ void fill_sse_rows(u16* p, size_t vol, int Wi) {   // SSEi<7>::Init (
   }
 }
 
-struct SharedTables {   // one per process/device
+struct SharedTables {   // one per device: the tables are device memory and constant memory of THAT device
   bool ready = false;
-  int device = -1;
   float* d_logit = nullptr; float* d_lut12 = nullptr; u16* d_st = nullptr; u16* d_sq = nullptr; float* d_adam = nullptr;
   Tables T;
 };
-SharedTables g_tables;
+std::map<int, SharedTables> g_tables_by_device;
+std::mutex g_tables_mutex;
 
-int BuildSharedTables(int device) {
-  if (g_tables.ready && g_tables.device == device) return CMIXB200_OK;
+int BuildSharedTablesLocked(int device, SharedTables& g_tables);
+// Returns the table set of `device` (built on first use); the caller keeps a copy of .T in its predictor.
+int BuildSharedTables(int device, SharedTables** out) {
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
+  SharedTables& t = g_tables_by_device[device];
+  int r = t.ready ? CMIXB200_OK : BuildSharedTablesLocked(device, t);
+  if (r == CMIXB200_OK) *out = &t;
+  return r;
+}
+
+int BuildSharedTablesLocked(int device, SharedTables& g_tables) {
+  (void)device;
   std::vector<float> logit(100001);
   for (int i = 0; i < 100001; ++i) {
     float p = (i + 0.5f) / 100001;
@@ -247,8 +261,9 @@ int BuildSharedTables(int device) {
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   CK(cudaFuncSetAttribute(ppmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PPMD_WARPS * sizeof(PpmdWarpShared))));
   CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
+  CK(cudaFuncSetAttribute(fxcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
+  CK(cudaFuncSetAttribute(fxcm_bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
   g_tables.ready = true;
-  g_tables.device = device;
   return CMIXB200_OK;
 }
 
@@ -284,6 +299,15 @@ struct cmixb200_predictor {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_ev;
   u8 vocab[256];
   int V = 0;
+  Tables T;                            // this device's shared read-only tables (copied at create: no global is read at launch)
+  SharedTables* shared = nullptr;
+  // resident FXCM (fxcm.cuh): device state, its text block and tables; `replay_mask` = CMIXB200_REPLAY_* flags of create_ex
+  unsigned replay_mask = 0;
+  std::string dict_path;
+  fx::State* d_fx = nullptr; fx::TextState* d_fx_text = nullptr; fx::Tables* d_fx_tables = nullptr;
+  cudaStream_t s_fx = nullptr;
+  u16* d_ext_gen = nullptr; size_t ext_gen_bits = 0; u32* d_lstm_fx = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // reusable ordering events (LaunchChunk)
 
   template <class T> int Alloc(T** p, size_t n, bool zero = true) {
     void* q = nullptr;
@@ -307,6 +331,53 @@ int InitDirect(cmixb200_predictor* P, DirectTable& d, int limit, float delta, u6
   d.checksum = nullptr;
   if (hashed) TRY(P->Alloc(&d.checksum, rows));
   return CMIXB200_OK;
+}
+
+__global__ void fill_u16(u16* p, size_t n, u16 v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// Memory backend of fx::build_state (fxcm_host.h): zeroed cudaMalloc, fill kernels, blocking uploads.
+struct DeviceBackend {
+  cmixb200_predictor* P; bool ok = true;
+  void* alloc(size_t bytes) { u8* q = nullptr; if (P->Alloc(&q, bytes ? bytes : 1) != CMIXB200_OK) { ok = false; return nullptr; } return q; }
+  void fill16(void* p, size_t n, u16 v) { fill_u16<<<1024, 256>>>((u16*)p, n, v); }
+  void fill32(void* p, size_t n, u32 v) { fill_u32<<<1024, 256>>>((u32*)p, n, v); }
+  void upload(void* d, const void* s, size_t bytes) { if (cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice) != cudaSuccess) ok = false; }
+};
+
+// The resident FXCM model: tables built on the host with the oracle's glibc, ~4.6 GB of bucket tables,
+// mixer weights and APMs in HBM, the WRT dictionary (runner.cpp:17's dictionary_path side channel) as flat text.
+int BuildFxcm(cmixb200_predictor* P) {
+  fx::Tables* T = new fx::Tables();
+  fx::build_tables(*T);
+  fx::HostDict D;
+  D.load(P->dict_path.empty() ? nullptr : P->dict_path.c_str());
+  if (!P->dict_path.empty() && !D.loaded) { delete T; g_last_error = "cannot read dictionary " + P->dict_path; return CMIXB200_ERR_ARG; }
+  if (D.loaded) {
+    char* d_chars = nullptr; u32* d_off = nullptr;
+    TRY(P->Alloc(&d_chars, D.chars.size() + 1, false));
+    TRY(P->Alloc(&d_off, D.off.size() + 1, false));
+    CK(cudaMemcpy(d_chars, D.chars.data(), D.chars.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off, D.off.data(), D.off.size() * 4, cudaMemcpyHostToDevice));
+    T->dict_chars = d_chars; T->dict_off = d_off; T->dict_n = (int)D.off.size(); T->dict_loaded = 1;
+  }
+  TRY(P->Alloc(&P->d_fx_tables, 1, false));
+  CK(cudaMemcpy(P->d_fx_tables, T, sizeof *T, cudaMemcpyHostToDevice));
+  fx::State* S = new fx::State();
+  fx::TextState* X = new fx::TextState();
+  DeviceBackend be{P};
+  const bool built = fx::build_state(be, *T, *S, *X) && be.ok;
+  int r = CMIXB200_OK;
+  if (!built) { if (g_last_error.empty()) g_last_error = "FXCM state allocation failed"; r = CMIXB200_ERR_CUDA; }
+  if (r == CMIXB200_OK) r = P->Alloc(&P->d_fx, 1, false);
+  if (r == CMIXB200_OK) r = P->Alloc(&P->d_fx_text, 1, false);
+  if (r == CMIXB200_OK) {
+    S->text = P->d_fx_text; S->T = P->d_fx_tables;
+    if (cudaMemcpy(P->d_fx, S, sizeof *S, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(P->d_fx_text, X, sizeof *X, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "FXCM state upload failed"; r = CMIXB200_ERR_CUDA; }
+  }
+  delete S; delete X; delete T;
+  return r;
 }
 
 int BuildStream(cmixb200_predictor* P) {
@@ -343,7 +414,7 @@ int BuildStream(cmixb200_predictor* P) {
     TRY(P->Alloc(&S.x2, kMix2Vol, false));
     fill_u32<<<512, 256>>>((u32*)S.x1, kMix1Vol, 7649 + 16384);
     fill_u32<<<512, 256>>>((u32*)S.x2, kMix2Vol, 2561 + 16384);
-    S.st = g_tables.d_st; S.sq = g_tables.d_sq;
+    S.st = P->shared->d_st; S.sq = P->shared->d_sq;
     S.j = 1; S.pc = 0; S.ffl = 0;
   }
   // ---------------- small models + contexts (construction order == rand() order) ----------------
@@ -411,7 +482,7 @@ int BuildStream(cmixb200_predictor* P) {
     for (int i = 0; i < 256; ++i) L.bm.probs[i] = 1.0 / 256;
     L.bm.top = 255;
     L.hidden[2 * C] = 1;
-    L.adam = g_tables.d_adam;
+    L.adam = P->shared->d_adam;
     TRY(P->Alloc(&L.out_w, (size_t)H * V * LSTM_HID));
     TRY(P->Alloc(&L.output, (size_t)H * V, false));
     fill_f32<<<64, 256>>>(L.output, (size_t)H * V, (float)(1.0 / V));
@@ -471,20 +542,32 @@ int BuildStream(cmixb200_predictor* P) {
     h.ppmd = P->d_ppmd_model;
   }
   CK(cudaMemcpy(P->d_st, &h, sizeof h, cudaMemcpyHostToDevice));
+  if (!(P->replay_mask & CMIXB200_REPLAY_FXCM)) TRY(BuildFxcm(P));
   CK(cudaDeviceSynchronize());
   return CMIXB200_OK;
 }
 
 int EnsureScratch(cmixb200_predictor* P, size_t n_bytes) {
   const size_t bits = n_bytes * 8;
-  if (bits <= P->scratch_bits) return CMIXB200_OK;
-  for (void* q : {(void*)P->d_small_x, (void*)P->d_sel, (void*)P->d_lstm_x, (void*)P->d_decay, (void*)P->d_p}) if (q) cudaFree(q);
-  CK(cudaMalloc(&P->d_small_x, bits * SMALL_X_PITCH * 4));
-  CK(cudaMalloc(&P->d_sel, bits * SEL_PITCH * 4));
-  CK(cudaMalloc(&P->d_lstm_x, bits * 2 * 4));
-  CK(cudaMalloc(&P->d_decay, bits * 4));
-  CK(cudaMalloc(&P->d_p, bits * 4));
-  P->scratch_bits = bits;
+  if (bits > P->scratch_bits) {
+    for (void* q : {(void*)P->d_small_x, (void*)P->d_sel, (void*)P->d_lstm_x, (void*)P->d_decay, (void*)P->d_p, (void*)P->d_lstm_fx}) if (q) cudaFree(q);
+    P->d_small_x = nullptr; P->d_sel = nullptr; P->d_lstm_x = nullptr; P->d_decay = nullptr; P->d_p = nullptr; P->d_lstm_fx = nullptr;
+    P->scratch_bits = 0;                       // a failed allocation below must not leave freed pointers behind
+    CK(cudaMalloc(&P->d_small_x, bits * SMALL_X_PITCH * 4));
+    CK(cudaMalloc(&P->d_sel, bits * SEL_PITCH * 4));
+    CK(cudaMalloc(&P->d_lstm_x, bits * 2 * 4));
+    CK(cudaMalloc(&P->d_decay, bits * 4));
+    CK(cudaMalloc(&P->d_p, bits * 4));
+    CK(cudaMalloc(&P->d_lstm_fx, bits * 4));
+    P->scratch_bits = bits;
+  }
+  if (P->d_fx && bits > P->ext_gen_bits) {     // codes of the resident models: 4 KB per coded bit
+    if (P->d_ext_gen) cudaFree(P->d_ext_gen);
+    P->d_ext_gen = nullptr; P->ext_gen_bits = 0;
+    CK(cudaMalloc(&P->d_ext_gen, bits * N_EXT * 2));
+    CK(cudaMemset(P->d_ext_gen, 0xFF, bits * N_EXT * 2));   // 0xFFFF = "0.5": slots of a model that is neither resident nor replayed
+    P->ext_gen_bits = bits;
+  }
   return CMIXB200_OK;
 }
 
@@ -506,44 +589,48 @@ void HarvestMixTimes(cmixb200_predictor* P) {
   P->pending_ev.clear();
 }
 
-// Launch the three bulk kernels for a batch of streams whose ChunkArgs are already on the device.
+// Launch the bulk kernels of one sub-chunk for a batch of streams whose ChunkArgs are already on the device:
+// ppmd -> (small | lstm -> fxcm) -> mix [-> encode], each on its own CUDA stream of the group's lead predictor.
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false,
-                bool with_ppmd = false) {
-  const Tables T = g_tables.T;
+                bool with_ppmd = false, bool with_fx = false) {
+  const Tables T = lead->T;
+  for (int i = 0; i < 8; ++i) if (!lead->ev[i]) CK(cudaEventCreateWithFlags(&lead->ev[i], cudaEventDisableTiming));
   if (with_ppmd && !pretrain) {
     // the PPMD producer runs ahead on its own stream; both consumers of its distributions wait for this sub-chunk's
     ppmd_kernel<<<(n_streams + PPMD_WARPS - 1) / PPMD_WARPS, PPMD_WARPS * 32, PPMD_WARPS * sizeof(PpmdWarpShared), lead->s_ppmd>>>(d_args, n_streams);
     lead->launches++;
-    cudaEvent_t e0;
-    CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-    CK(cudaEventRecord(e0, lead->s_ppmd));
-    CK(cudaStreamWaitEvent(lead->s_small, e0, 0));
-    CK(cudaStreamWaitEvent(lead->s_lstm, e0, 0));
-    CK(cudaEventDestroy(e0));
+    CK(cudaEventRecord(lead->ev[0], lead->s_ppmd));
+    CK(cudaStreamWaitEvent(lead->s_small, lead->ev[0], 0));
+    CK(cudaStreamWaitEvent(lead->s_lstm, lead->ev[0], 0));
   }
   small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
   lead->launches++;
-  if (!pretrain) {
+  if (pretrain) {
+    if (with_fx) { fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args); lead->launches++; }
+  } else {
     lstm_kernel<<<LSTM_CTAS * n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
     lead->launches++;
-    // the mixer consumes what the two producers write: order it after both
-    cudaEvent_t e1, e2;
-    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-    CK(cudaEventRecord(e1, lead->s_small));
-    CK(cudaEventRecord(e2, lead->s_lstm));
-    CK(cudaStreamWaitEvent(lead->s_mix, e1, 0));
-    CK(cudaStreamWaitEvent(lead->s_mix, e2, 0));
-    static const bool use_v1 = getenv("CMIXB200_MIX_V1") != nullptr;   // barrier-per-phase reference version of the kernel
+    CK(cudaEventRecord(lead->ev[1], lead->s_small));
+    CK(cudaEventRecord(lead->ev[2], lead->s_lstm));
+    if (with_fx) {
+      // FXCM consumes the LSTM's bit read-outs of this sub-chunk (lstmpr / lstmex) and produces 431 codes per bit
+      CK(cudaStreamWaitEvent(lead->s_fx, lead->ev[2], 0));
+      fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args);
+      lead->launches++;
+      CK(cudaEventRecord(lead->ev[3], lead->s_fx));
+      CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[3], 0));
+    }
+    // the mixer consumes what the producers write: order it after all of them
+    CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[1], 0));
+    CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[2], 0));
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (lead->time_mix) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, lead->s_mix)); }
-    if (use_v1) mix_kernel<<<2 * n_streams, MIX_THREADS, sizeof(MixShared), lead->s_mix>>>(d_args, T);
-    else mix_kernel_v3<<<2 * n_streams, MIX_THREADS, sizeof(MixShared3), lead->s_mix>>>(d_args, T);
+    mix_kernel_v3<<<2 * n_streams, MIX_THREADS, sizeof(MixShared3), lead->s_mix>>>(d_args, T);
     lead->launches++;
     if (lead->time_mix) { CK(cudaEventRecord(t1, lead->s_mix)); lead->pending_ev.push_back({t0, t1}); }
     if (with_coder) { encode_kernel<<<n_streams, 32, 0, lead->s_mix>>>(d_args); lead->launches++; }
-    CK(cudaEventDestroy(e1));
-    CK(cudaEventDestroy(e2));
+    // the producers of the NEXT sub-chunk overwrite nothing the mixer still reads (scratch is indexed by bit), except
+    // the LSTM feedback FXCM reads: it is per-bit scratch too, so no back edge is needed.
   }
   CK(cudaGetLastError());
   return CMIXB200_OK;
@@ -579,13 +666,15 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
   u64 decay_steps0 = 0;
-  bool any_coder = false, any_ppmd = false;
+  bool any_coder = false, any_ppmd = false, any_fx = false;
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
     if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
+    if ((P->d_fx != nullptr) != (lead->d_fx != nullptr)) { g_last_error = "bulk coding: streams of one batch must agree on which models are resident"; return CMIXB200_ERR_ARG; }
+    if (P->s_fx) CK(cudaStreamSynchronize(P->s_fx));
     CK(cudaStreamSynchronize(P->s_mix));                 // a lock-step Perceive() may still be in flight
     CK(cudaStreamSynchronize(P->s_small));
-    TRY(EnsureScratch(P, n_bytes));
+    if (!pretrain) TRY(EnsureScratch(P, n_bytes));      // Pretrain() touches models and contexts only: no per-bit scratch
     if (!pretrain && !(d_ppmd && d_ppmd[s]) && P->ppmd_gen_bytes < n_bytes) {
       if (P->d_ppmd_gen) cudaFree(P->d_ppmd_gen);
       P->d_ppmd_gen = nullptr; P->ppmd_gen_bytes = 0;
@@ -604,15 +693,23 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
       memset(&a, 0, sizeof a);
       a.st = P->d_st; a.bytes = d_bytes[s] + off;
       a.ext = (d_ext && d_ext[s]) ? d_ext[s] + off * 8 * N_EXT : nullptr;
+      if (P->d_fx) {                                               // resident FXCM: the mixer stages from the generated codes
+        a.fx = P->d_fx;
+        a.ext_replay = a.ext;
+        if (!pretrain) { a.ext_gen = P->d_ext_gen + off * 8 * N_EXT; a.ext = a.ext_gen; a.lstm_fx = P->d_lstm_fx + off * 8; }
+        any_fx = true;
+      }
       a.ppmd = (d_ppmd && d_ppmd[s]) ? d_ppmd[s] + off * 256 : nullptr;
       if (!a.ppmd && !pretrain) {                                   // no replay: the resident model produces the distributions
         a.ppmd_gen = P->d_ppmd_gen + off * 256;
         a.ppmd = a.ppmd_gen;
         any_ppmd = true;
       }
-      a.decay = P->d_decay + off * 8;
-      a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
-      a.lstm_x = P->d_lstm_x + off * 8 * 2;
+      if (!pretrain) {
+        a.decay = P->d_decay + off * 8;
+        a.small_x = P->d_small_x + off * 8 * SMALL_X_PITCH; a.sel = P->d_sel + off * 8 * SEL_PITCH;
+        a.lstm_x = P->d_lstm_x + off * 8 * 2;
+      }
       a.p_out = (d_p_out && d_p_out[s]) ? d_p_out[s] + off * 8 : nullptr;
       if (P->coder_on && !pretrain) {
         a.coder = P->d_coder;
@@ -636,11 +733,12 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   for (size_t k = 0; k < n_sub; ++k)
     for (int g0 = 0; g0 < n_streams; g0 += gsz) {
       const int cnt = n_streams - g0 < gsz ? n_streams - g0 : gsz;
-      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder, any_ppmd));
+      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder, any_ppmd, any_fx));
     }
   for (int g0 = 0; g0 < n_streams; g0 += gsz) {
     cmixb200_predictor* G = preds[g0];
     CK(cudaStreamSynchronize(G->s_small));
+    if (any_fx) CK(cudaStreamSynchronize(G->s_fx));
     if (!pretrain) {
       if (any_ppmd) CK(cudaStreamSynchronize(G->s_ppmd));
       CK(cudaStreamSynchronize(G->s_lstm));
@@ -659,9 +757,32 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   return CMIXB200_OK;
 }
 
+// Bulk calls are cut into pieces so that the per-bit scratch (4 KB of model codes per coded bit when a model is resident)
+// stays bounded whatever n_bytes the caller passes; a piece is long enough (16 k bits) to amortise the pipeline fill.
+const size_t kMaxPiece = 2048;
+
+int RunPieces(cmixb200_predictor** preds, int n_streams, const u8* const* d_bytes, size_t n_bytes, const u16* const* d_ext,
+              const float* const* d_ppmd, float* const* d_p_out, bool pretrain) {
+  bool bounded = false;                       // only the codes of resident models need per-bit scratch worth bounding
+  for (int s = 0; s < n_streams; ++s) bounded = bounded || preds[s]->d_fx != nullptr;
+  if (pretrain || !bounded || n_bytes <= kMaxPiece) return RunPipelined(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, pretrain);
+  std::vector<const u8*> b(n_streams); std::vector<const u16*> e(n_streams); std::vector<const float*> q(n_streams); std::vector<float*> o(n_streams);
+  for (size_t off = 0; off < n_bytes; off += kMaxPiece) {
+    const size_t n = n_bytes - off < kMaxPiece ? n_bytes - off : kMaxPiece;
+    for (int s = 0; s < n_streams; ++s) {
+      b[s] = d_bytes[s] + off;
+      e[s] = (d_ext && d_ext[s]) ? d_ext[s] + off * 8 * N_EXT : nullptr;
+      q[s] = (d_ppmd && d_ppmd[s]) ? d_ppmd[s] + off * 256 : nullptr;
+      o[s] = (d_p_out && d_p_out[s]) ? d_p_out[s] + off * 8 : nullptr;
+    }
+    TRY(RunPipelined(preds, n_streams, b.data(), n, d_ext ? e.data() : nullptr, d_ppmd ? q.data() : nullptr, d_p_out ? o.data() : nullptr, false));
+  }
+  return CMIXB200_OK;
+}
+
 int CodeDevice(cmixb200_predictor* P, const u8* d_bytes, size_t n_bytes, const u16* d_ext, const float* d_ppmd,
                float* d_p_out, bool pretrain) {
-  return RunPipelined(&P, 1, &d_bytes, n_bytes, &d_ext, &d_ppmd, &d_p_out, pretrain);
+  return RunPieces(&P, 1, &d_bytes, n_bytes, &d_ext, &d_ppmd, &d_p_out, pretrain);
 }
 
 }  // namespace
@@ -671,15 +792,23 @@ extern "C" {
 const char* cmixb200_last_error(void) { return g_last_error.c_str(); }
 
 int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int device, cmixb200_predictor** out) {
-  (void)dictionary_path;   // consumed by FXCM only (fxcmv1.cpp:412-428), which is replayed, not resident
+  return cmixb200_create_ex(vocab, dictionary_path, device, 0, out);
+}
+
+int cmixb200_create_ex(const uint8_t vocab[256], const char* dictionary_path, int device, unsigned replay_mask, cmixb200_predictor** out) {
   if (!vocab || !out) { g_last_error = "null argument"; return CMIXB200_ERR_ARG; }
+  replay_mask |= CMIXB200_REPLAY_PAQ8;   // PAQ8 is not resident yet: its 1591 slots are replayed or 0.5
   int n_dev = 0;
   CK(cudaGetDeviceCount(&n_dev));
   if (device < 0 || device >= n_dev) { g_last_error = "no such CUDA device"; return CMIXB200_ERR_CUDA; }
   CK(cudaSetDevice(device));
-  TRY(BuildSharedTables(device));
+  SharedTables* shared = nullptr;
+  TRY(BuildSharedTables(device, &shared));
   cmixb200_predictor* P = new cmixb200_predictor();
   P->device = device;
+  P->shared = shared; P->T = shared->T;
+  P->replay_mask = replay_mask;
+  if (dictionary_path) P->dict_path = dictionary_path;
   for (int i = 0; i < 256; ++i) { P->vocab[i] = vocab[i] ? 1 : 0; P->V += P->vocab[i]; }
   if (P->V == 0) { delete P; g_last_error = "empty vocabulary"; return CMIXB200_ERR_ARG; }
   int r = BuildStream(P);
@@ -694,11 +823,13 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
     cudaStreamCreateWithPriority(&P->s_lstm, cudaStreamNonBlocking, p_lstm);
     cudaStreamCreateWithPriority(&P->s_mix, cudaStreamNonBlocking, p_mix);
     cudaStreamCreateWithPriority(&P->s_ppmd, cudaStreamNonBlocking, p_mix);      // one warp per stream, must never be the one waited for
+    cudaStreamCreateWithPriority(&P->s_fx, cudaStreamNonBlocking, p_small);
     cudaEventCreateWithFlags(&P->ev_lock_mix, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_lock_small, cudaEventDisableTiming);
     cudaEventRecord(P->ev_lock_mix, P->s_mix);
     if (cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
         cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
+    else cudaMemset(P->d_ext_bit, 0xFF, N_EXT * 2);
   }
   if (r != CMIXB200_OK) { cmixb200_destroy(P); return r; }
   *out = P;
@@ -720,6 +851,10 @@ void cmixb200_destroy(cmixb200_predictor* P) {
   if (P->d_coder) cudaFree(P->d_coder);
   if (P->d_code) cudaFree(P->d_code);
   if (P->s_ppmd) cudaStreamDestroy(P->s_ppmd);
+  if (P->s_fx) cudaStreamDestroy(P->s_fx);
+  for (int i = 0; i < 8; ++i) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
+  if (P->d_ext_gen) cudaFree(P->d_ext_gen);
+  if (P->d_lstm_fx) cudaFree(P->d_lstm_fx);
   if (P->d_ppmd_gen) cudaFree(P->d_ppmd_gen);
   if (P->s_copy) cudaStreamDestroy(P->s_copy);
   if (P->s_small) cudaStreamDestroy(P->s_small);
@@ -730,19 +865,24 @@ void cmixb200_destroy(cmixb200_predictor* P) {
 
 int cmixb200_feed_external_bit(cmixb200_predictor* P, const uint16_t* codes) {
   CK(cudaSetDevice(P->device));
-  CK(cudaMemcpy(P->d_ext_bit, codes, N_EXT * 2, cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(P->s_mix));           // the resident models of the previous Perceive() write d_ext_bit on s_mix
+  // slots of resident models are produced on the device; only the replayed ones are taken from the caller
+  const size_t first = P->d_fx ? fx::N_OUT : 0;
+  CK(cudaMemcpy(P->d_ext_bit + first, codes + first, (N_EXT - first) * 2, cudaMemcpyHostToDevice));
   P->ext_bit_valid = true;
   return CMIXB200_OK;
 }
 int cmixb200_feed_external_byte(cmixb200_predictor* P, const float* ppmd256) {
   CK(cudaSetDevice(P->device));
+  CK(cudaStreamSynchronize(P->s_mix));           // small_perceive / lstm_byte kernels of the previous byte read d_ppmd_byte
+  CK(cudaStreamSynchronize(P->s_small));
   CK(cudaMemcpy(P->d_ppmd_byte, ppmd256, 256 * 4, cudaMemcpyHostToDevice));
   P->ppmd_byte_valid = true;
   return CMIXB200_OK;
 }
 
 float cmixb200_predict(cmixb200_predictor* P) {
-  const Tables T = g_tables.T;
+  const Tables T = P->T;
   if (cudaSetDevice(P->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1.0f; }
   // 3 launches: producers (small models || LSTM read-out), 26 row CTAs (one serial chain each), final stage
   // the producers run on s_small (behind the previous small_perceive), after the previous bit's mixer/LSTM update
@@ -750,13 +890,17 @@ float cmixb200_predict(cmixb200_predictor* P) {
   lock_predict_inputs_kernel<<<2, 64, 0, P->s_small>>>(P->d_st, T);
   cudaEventRecord(P->ev_lock_small, P->s_small);
   cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0);
-  mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, P->ext_bit_valid ? P->d_ext_bit : nullptr);
+  mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, (P->ext_bit_valid || P->d_fx) ? P->d_ext_bit : nullptr);
   mix_predict_final_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T);
   P->launches += 3;
   float p = -1.0f;
   cudaError_t e = cudaMemcpyAsync(&p, &P->d_st->last_p, 4, cudaMemcpyDeviceToHost, P->s_mix);
   if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
   if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
+  if (P->ext_bit_valid) {   // replayed slots fall back to "0.5" until they are fed again
+    const size_t first = P->d_fx ? fx::N_OUT : 0;
+    cudaMemsetAsync(P->d_ext_bit + first, 0xFF, (N_EXT - first) * 2, P->s_mix);
+  }
   P->ext_bit_valid = false;
   return p;
 }
@@ -780,6 +924,8 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, ppmd, 0);      // concurrent with the mixer / LSTM update
   mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
   if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
+  // FXCM is perceived last and sees the LSTM's read-out of the next bit (predictor.cpp:462-466)
+  if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 0, P->d_ext_bit); P->launches++; }
   CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
   P->launches += 2;
   CK(cudaGetLastError());
@@ -792,11 +938,12 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
 int cmixb200_pretrain(cmixb200_predictor* P, int bit) {
   CK(cudaSetDevice(P->device));
   bit = bit ? 1 : 0;
-  const Tables T = g_tables.T;
+  const Tables T = P->T;
   const bool byte_done = P->bit_context >= 128;
   small_predict_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, T);
   small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, nullptr, 1);
   P->launches += 2;
+  if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 1, P->d_ext_bit); P->launches++; }
   CK(cudaGetLastError());
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   return CMIXB200_OK;
@@ -841,7 +988,7 @@ int cmixb200_pretrain_bytes(cmixb200_predictor* P, const uint8_t* bytes, size_t 
 
 int cmixb200_code_batch_device(cmixb200_predictor** preds, int n_streams, const uint8_t* const* d_bytes, size_t n_bytes,
                                const uint16_t* const* d_ext, const float* const* d_ppmd, float* const* d_p_out) {
-  return RunPipelined(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, false);
+  return RunPieces(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, false);
 }
 
 int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t* const* bytes, size_t n_bytes,
@@ -936,6 +1083,7 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
   CK(cudaSetDevice(P->device));
   CK(cudaStreamSynchronize(P->s_mix));
   CK(cudaStreamSynchronize(P->s_small));
+  if (P->s_fx) CK(cudaStreamSynchronize(P->s_fx));
   const void* src = nullptr;
   switch (what) {
     case CMIXB200_DBG_SMALL_X: src = P->d_small_x; break;
@@ -948,6 +1096,10 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
     case CMIXB200_DBG_PPMD_BULK:
       if (bytes > P->ppmd_gen_bytes * 256 * sizeof(float)) { g_last_error = "debug_fetch: more PPMD rows than the last bulk call produced"; return CMIXB200_ERR_ARG; }
       src = P->d_ppmd_gen; break;
+    case CMIXB200_DBG_EXT_GEN:
+      if (!P->d_ext_gen || bytes > P->ext_gen_bits * N_EXT * 2) { g_last_error = "debug_fetch: no generated codes of that size"; return CMIXB200_ERR_ARG; }
+      src = P->d_ext_gen; break;
+    case CMIXB200_DBG_EXT_BIT: src = P->d_ext_bit; break;
     case CMIXB200_DBG_PROFILE:
       if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 64 * 8)); CK(cudaMemset(P->d_prof, 0, 64 * 8)); }
       src = P->d_prof; break;

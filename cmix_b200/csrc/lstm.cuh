@@ -618,6 +618,14 @@ __device__ void lstm_readout(LstmState& S, const Tables& T, float* x_out, float*
   *override_out = (p == 0.0f || p == 1.0f) ? p : -1.0f;
   *x_out = stretch(T, p);
 }
+// lstmpr = Discretize(p) = 1 + 4094 * p truncated (predictor.cpp:180-182), lstmex = first arg-max of the byte range
+// (byte-model.cpp:13-20), packed as lstmpr | lstmex << 16.
+__device__ __forceinline__ u32 lstm_feedback(const float* probs, int bot, int top, float p) {
+  int ex = bot; float best = probs[bot];
+  for (int i = bot + 1; i <= top; ++i) if (probs[i] > best) { best = probs[i]; ex = i; }
+  const u32 pr = (u32)XM_FADD(1.0f, XM_FMUL(4094.0f, p));
+  return (pr & 0xffffu) | ((u32)ex << 16);
+}
 __device__ void bm_perceive(ByteModelState& b, int bit) {
   b.mid = b.bot + ((b.top - b.bot) / 2);
   if (bit) b.bot = b.mid + 1; else b.top = b.mid;
@@ -654,9 +662,15 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
         const u64 t = (u64)pos * 8 + tid;
         a.lstm_x[2 * t] = stretch(T, p);
         a.lstm_x[2 * t + 1] = (p == 0.0f || p == 1.0f) ? p : -1.0f;
+        // FXCM's feedback (predictor.cpp:462-465): the read-out of bit t is what FXCM sees while perceiving bit t-1
+        if (a.lstm_fx && tid > 0) a.lstm_fx[t - 1] = lstm_feedback(sh.probs256, bot, top, p);
       }
     }
     lstm_byte_update(cluster, S, a.ppmd ? a.ppmd + (u64)pos * 256 : nullptr, byte, sh, rank, tid, prof, &tprev);
+    if (a.lstm_fx && rank == 0 && tid == 0) {   // first bit of the next byte: range [0,255] whatever that byte is
+      int ex; const float p = bytemodel_predict(sh.probs256, 0, 255, &ex);
+      a.lstm_fx[(u64)pos * 8 + 7] = lstm_feedback(sh.probs256, 0, 255, p);
+    }
   }
   lstm_store_cache(S, sh, rank, tid);
   __threadfence();

@@ -200,7 +200,7 @@ __device__ __forceinline__ void stage_inputs(float* x, const Tables& T, const u1
     if (k < 3) v = small_x[k];
     else if (k < 3 + N_EXT) {
       const u32 code = ext ? ext[k - 3] : 0xFFFFu;
-      v = T.lut12[code == 0xFFFFu ? 4096 : code];
+      v = T.lut12[code == 0xFFFFu ? 4096 : (code > 4095u ? 4095u : code)];
     }
     else if (k < 2076) v = small_x[k - N_EXT];
     else if (k == 2076) v = small_x[N_SMALL];

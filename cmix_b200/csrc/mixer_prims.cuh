@@ -103,7 +103,7 @@ __device__ __forceinline__ void stage_inputs_v2(float* x, const float* lut, cons
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
     const int k = mtid + q * NT;
-    if (k < N_INPUTS) x[k] = code[q] == 0x10000u ? direct[q] : lut[code[q] == 0xFFFFu ? 4096 : code[q]];
+    if (k < N_INPUTS) x[k] = code[q] == 0x10000u ? direct[q] : lut[code[q] == 0xFFFFu ? 4096 : (code[q] > 4095u ? 4095u : code[q])];
   }
 }
 

@@ -12,6 +12,7 @@
 #include "ppmd_model.h"
 
 namespace cmixb200 {
+namespace fx { struct State; }     // resident FXCM model (fxcm_model.h)
 
 typedef uint64_t u64;
 typedef uint32_t u32;
@@ -148,6 +149,7 @@ struct StreamState {
   float small_x[SMALL_X_PITCH];
   PpmdModel* ppmd;              // resident PPMD model (ppmd_model.h); its arenas are separate allocations
   float lstm_x, lstm_override;  // override: -1 none, else 0 or 1 (predictor.cpp:383)
+  u32 lstm_fx;                  // lock-step: lstmpr | lstmex << 16 of the next bit (predictor.cpp:462-465)
   float last_p;
 };
 
@@ -180,6 +182,13 @@ struct ChunkArgs {
   float* p_out;                 // [n_bytes*8] result
   u32 n_bytes;
   u32 pretrain;                 // 1: Pretrain() semantics (models + contexts only)
+  // resident FXCM / PAQ8 (fxcm.cuh, paq8.cuh): they write their 12-bit codes into ext_gen ([n_bytes*8][N_EXT]); `ext` above is
+  // then == ext_gen. Slots of a model that is NOT resident are copied from ext_replay (the caller's replayed codes) when given.
+  fx::State* fx;                // null = FXCM replayed
+  void* paq8;                   // null = PAQ8 replayed
+  u16* ext_gen;
+  const u16* ext_replay;
+  u32* lstm_fx;                 // [n_bytes*8] lstmpr | lstmex << 16 FXCM consumes while perceiving bit t (written by the LSTM kernel)
   CoderState* coder;            // optional device arithmetic coder fed with (p_out, bit); null = off
   unsigned long long* prof;     // optional [32] per-phase SM-cycle accumulators (null = off)
 };

@@ -38,6 +38,13 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
                     cmixb200_predictor** out);
 void cmixb200_destroy(cmixb200_predictor*);
 
+/* Same, choosing which of the big model groups are REPLAYED instead of device resident (test and A/B hook: a replayed
+ * group costs no HBM and takes its outputs from cmixb200_feed_external_* / the `ext` / `ppmd` arguments of the bulk calls;
+ * without them its inputs carry p = 0.5). cmixb200_create == replay_mask 0 == everything that is resident is used. */
+enum { CMIXB200_REPLAY_FXCM = 1, CMIXB200_REPLAY_PAQ8 = 2 };
+int cmixb200_create_ex(const uint8_t vocab[256], const char* dictionary_path, int device, unsigned replay_mask,
+                       cmixb200_predictor** out);
+
 /* float Predictor::Predict() (predictor.cpp:361). Returns -1 on failure. */
 float cmixb200_predict(cmixb200_predictor*);
 /* void Predictor::Perceive(int bit) (predictor.cpp:421). */
@@ -95,6 +102,8 @@ enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, 
        CMIXB200_DBG_PROFILE = 6 /* 64 u64 per-phase cycle counters; first fetch enables them */,
        CMIXB200_DBG_PPMD_PROBS = 7 /* 256 f32: the resident PPMD model's distribution after the last lock-step byte */,
        CMIXB200_DBG_PPMD_PROFILE = 9 /* 6 u64: cycles in symbol search, model update, suffix walk, ConvertSQ, emit; bytes */,
+       CMIXB200_DBG_EXT_GEN = 10 /* [n_bytes*8][2022] u16: the codes the resident models wrote in the last bulk piece (<= 2048 bytes) */,
+       CMIXB200_DBG_EXT_BIT = 11 /* [2022] u16: lock-step codes for the next Predict() */,
        CMIXB200_DBG_PPMD_BULK = 8 /* [n_bytes][256] f32: the distributions the resident model produced in the last bulk call */ };
 int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
 

@@ -13,6 +13,7 @@ from conftest import ROOT, Golden, port_replay, synthetic_streams
 pytestmark = pytest.mark.gpu
 
 TOL = 0.0   # probabilities must match bit for bit; the spec's tolerance is 1e-5
+REPLAY_ALL = ("fxcm", "paq8")   # tests driven by synthetic code streams replay the big model groups instead of running them
 
 
 @pytest.fixture(scope="module")
@@ -79,7 +80,7 @@ def test_cuda_matches_oracle_port_on_seeded_inputs(cm, port):
     """No reference needed: synthetic replay streams, ragged vocabulary, 3 BPTT rounds."""
     stream, vocab, codes, ppmd = synthetic_streams(330, seed=11)
     want, want_lstm = port_replay(port, vocab, stream, codes, ppmd, want_lstm=True)
-    P = cm.Predictor(vocab)
+    P = cm.Predictor(vocab, replay=REPLAY_ALL)
     got = P.code_bytes(stream, codes, ppmd)
     assert np.abs(got - want).max() <= TOL
     assert np.array_equal(P.debug_fetch(4, (256,), np.float32), want_lstm)
@@ -98,7 +99,7 @@ def test_edge_cases(cm, port):
         codes = np.full((n * 8, 2022), 0xFFFF, dtype=np.uint16)
         ppmd = np.tile((vocab / vocab.sum()).astype(np.float32), (n, 1))
         want = port_replay(port, vocab, stream, codes, ppmd)
-        P = cm.Predictor(vocab)
+        P = cm.Predictor(vocab, replay=REPLAY_ALL)
         got = P.code_bytes(stream, codes, ppmd)
         assert np.array_equal(got, want)
         P.close()
@@ -119,7 +120,7 @@ def test_pretrain_then_code(cm, port):
     c = np.ascontiguousarray(codes); pp = np.ascontiguousarray(ppmd); s = np.ascontiguousarray(stream)
     port.op_run(Q, s.ctypes.data, s.size, c.ctypes.data, pp.ctypes.data, want.ctypes.data)
     port.op_destroy(Q)
-    P = cm.Predictor(vocab)
+    P = cm.Predictor(vocab, replay=REPLAY_ALL)
     P.pretrain_bytes(pre[:40].tobytes())             # bulk Pretrain ...
     for byte in pre[40:]:                            # ... and bit-by-bit Pretrain() agree
         for j in range(7, -1, -1):
@@ -134,10 +135,10 @@ def test_batch_of_streams_equals_individual_runs(cm):
     runs = [synthetic_streams(48, seed=s) for s in (21, 22, 23)]
     singles = []
     for stream, vocab, codes, ppmd in runs:
-        P = cm.Predictor(vocab)
+        P = cm.Predictor(vocab, replay=REPLAY_ALL)
         singles.append(P.code_bytes(stream, codes, ppmd))
         P.close()
-    preds = [cm.Predictor(r[1]) for r in runs]
+    preds = [cm.Predictor(r[1], replay=REPLAY_ALL) for r in runs]
     dev = torch.device("cuda:0")
     d_bytes = [torch.from_numpy(r[0]).to(dev) for r in runs]
     d_ext = [torch.from_numpy(r[2].view(np.int16)).to(dev) for r in runs]
@@ -158,7 +159,7 @@ def test_host_buffer_batch_crosses_the_staging_boundary(cm, port):
     n = 1100
     runs = [synthetic_streams(n, seed=s) for s in (31, 32)]
     want = [port_replay(port, r[1], r[0], r[2], r[3]) for r in runs]
-    preds = [cm.Predictor(r[1]) for r in runs]
+    preds = [cm.Predictor(r[1], replay=REPLAY_ALL) for r in runs]
     outs = [np.empty(n * 8, dtype=np.float32) for _ in runs]
     code_batch(preds, [r[0] for r in runs], n, [r[2] for r in runs], [r[3] for r in runs], outs)
     for p in preds:
@@ -199,7 +200,7 @@ def test_resident_ppmd_distributions_on_device(cm, name):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     n = min(12000, g["stream"].size)
     import torch
-    P = cm.Predictor(g["vocab"])
+    P = cm.Predictor(g["vocab"], replay=REPLAY_ALL)
     d_bytes = torch.from_numpy(g["stream"][:n].copy()).cuda()
     d_out = torch.empty(n * 8, dtype=torch.float32, device="cuda")
     P.code_bytes_device(d_bytes, n, None, None, d_out)          # one call: the debug fetch returns the last call's rows
@@ -218,10 +219,10 @@ def test_resident_ppmd_in_a_batch(cm):
     runs = [synthetic_streams(300, seed=s) for s in (41, 42, 43)]
     singles = []
     for stream, vocab, codes, _ in runs:
-        P = cm.Predictor(vocab)
+        P = cm.Predictor(vocab, replay=REPLAY_ALL)
         singles.append(P.code_bytes(stream, codes, None))
         P.close()
-    preds = [cm.Predictor(r[1]) for r in runs]
+    preds = [cm.Predictor(r[1], replay=REPLAY_ALL) for r in runs]
     dev = torch.device("cuda:0")
     d_bytes = [torch.from_numpy(r[0]).to(dev) for r in runs]
     d_ext = [torch.from_numpy(r[2].view(np.int16)).to(dev) for r in runs]
