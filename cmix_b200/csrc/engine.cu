@@ -30,6 +30,8 @@
 #include "coder.cuh"
 #include "fxcm.cuh"
 #include "fxcm_host.h"
+#include "paq8.cuh"
+#include "paq8_host.h"
 #include "lstm.cuh"
 #include "mixer.cuh"
 #include "mixer_v3.cuh"
@@ -263,6 +265,8 @@ int BuildSharedTablesLocked(int device, SharedTables& g_tables) {
   CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   CK(cudaFuncSetAttribute(fxcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
   CK(cudaFuncSetAttribute(fxcm_bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
+  CK(cudaFuncSetAttribute(paq8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P8Shared)));
+  CK(cudaFuncSetAttribute(paq8_bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P8Shared)));
   g_tables.ready = true;
   return CMIXB200_OK;
 }
@@ -306,6 +310,7 @@ struct cmixb200_predictor {
   std::string dict_path;
   fx::State* d_fx = nullptr; fx::TextState* d_fx_text = nullptr; fx::Tables* d_fx_tables = nullptr;
   cudaStream_t s_fx = nullptr;
+  p8::State* d_p8 = nullptr; p8::Tables* d_p8_tables = nullptr; cudaStream_t s_p8 = nullptr;   // resident PAQ8 (paq8.cuh)
   u16* d_ext_gen = nullptr; size_t ext_gen_bits = 0; u32* d_lstm_fx = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // reusable ordering events (LaunchChunk)
 
@@ -377,6 +382,26 @@ int BuildFxcm(cmixb200_predictor* P) {
         cudaMemcpy(P->d_fx_text, X, sizeof *X, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "FXCM state upload failed"; r = CMIXB200_ERR_CUDA; }
   }
   delete S; delete X; delete T;
+  return r;
+}
+
+// The resident PAQ8 model: ~10 GB of bucket tables, DMC nodes, mixer weight sets and the 1 GiB byte ring.
+int BuildPaq8(cmixb200_predictor* P) {
+  p8::Tables* T = new p8::Tables();
+  p8::build_tables(*T);
+  int r = P->Alloc(&P->d_p8_tables, 1, false);
+  if (r == CMIXB200_OK && cudaMemcpy(P->d_p8_tables, T, sizeof *T, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "PAQ8 table upload failed"; r = CMIXB200_ERR_CUDA; }
+  p8::State* S = new p8::State();
+  if (r == CMIXB200_OK) {
+    DeviceBackend be{P};
+    if (!(p8::build_state(be, *T, *S) && be.ok)) { if (g_last_error.empty()) g_last_error = "PAQ8 state allocation failed"; r = CMIXB200_ERR_CUDA; }
+  }
+  if (r == CMIXB200_OK) r = P->Alloc(&P->d_p8, 1, false);
+  if (r == CMIXB200_OK) {
+    S->T = P->d_p8_tables;
+    if (cudaMemcpy(P->d_p8, S, sizeof *S, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "PAQ8 state upload failed"; r = CMIXB200_ERR_CUDA; }
+  }
+  delete S; delete T;
   return r;
 }
 
@@ -543,6 +568,7 @@ int BuildStream(cmixb200_predictor* P) {
   }
   CK(cudaMemcpy(P->d_st, &h, sizeof h, cudaMemcpyHostToDevice));
   if (!(P->replay_mask & CMIXB200_REPLAY_FXCM)) TRY(BuildFxcm(P));
+  if (!(P->replay_mask & CMIXB200_REPLAY_PAQ8)) TRY(BuildPaq8(P));
   CK(cudaDeviceSynchronize());
   return CMIXB200_OK;
 }
@@ -561,7 +587,7 @@ int EnsureScratch(cmixb200_predictor* P, size_t n_bytes) {
     CK(cudaMalloc(&P->d_lstm_fx, bits * 4));
     P->scratch_bits = bits;
   }
-  if (P->d_fx && bits > P->ext_gen_bits) {     // codes of the resident models: 4 KB per coded bit
+  if ((P->d_fx || P->d_p8) && bits > P->ext_gen_bits) {     // codes of the resident models: 4 KB per coded bit
     if (P->d_ext_gen) cudaFree(P->d_ext_gen);
     P->d_ext_gen = nullptr; P->ext_gen_bits = 0;
     CK(cudaMalloc(&P->d_ext_gen, bits * N_EXT * 2));
@@ -592,7 +618,7 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 // Launch the bulk kernels of one sub-chunk for a batch of streams whose ChunkArgs are already on the device:
 // ppmd -> (small | lstm -> fxcm) -> mix [-> encode], each on its own CUDA stream of the group's lead predictor.
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false,
-                bool with_ppmd = false, bool with_fx = false) {
+                bool with_ppmd = false, bool with_fx = false, bool with_p8 = false) {
   const Tables T = lead->T;
   for (int i = 0; i < 8; ++i) if (!lead->ev[i]) CK(cudaEventCreateWithFlags(&lead->ev[i], cudaEventDisableTiming));
   if (with_ppmd && !pretrain) {
@@ -605,6 +631,10 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
   }
   small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
   lead->launches++;
+  if (with_p8) {   // PAQ8 depends on the coded bytes only: it starts at once on its own stream
+    paq8_kernel<<<n_streams, P8_THREADS, sizeof(P8Shared), lead->s_p8>>>(d_args);
+    lead->launches++;
+  }
   if (pretrain) {
     if (with_fx) { fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args); lead->launches++; }
   } else {
@@ -620,6 +650,7 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
       CK(cudaEventRecord(lead->ev[3], lead->s_fx));
       CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[3], 0));
     }
+    if (with_p8) { CK(cudaEventRecord(lead->ev[4], lead->s_p8)); CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[4], 0)); }
     // the mixer consumes what the producers write: order it after all of them
     CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[1], 0));
     CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[2], 0));
@@ -666,12 +697,13 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   std::vector<ChunkArgs> args(n_sub * n_streams);
   std::vector<float> decay;
   u64 decay_steps0 = 0;
-  bool any_coder = false, any_ppmd = false, any_fx = false;
+  bool any_coder = false, any_ppmd = false, any_fx = false, any_p8 = false;
   for (int s = 0; s < n_streams; ++s) {
     cmixb200_predictor* P = preds[s];
     if (P->device != lead->device || P->bit_context != 1) { g_last_error = "bulk coding: streams must share a device and start on a byte boundary"; return CMIXB200_ERR_ARG; }
-    if ((P->d_fx != nullptr) != (lead->d_fx != nullptr)) { g_last_error = "bulk coding: streams of one batch must agree on which models are resident"; return CMIXB200_ERR_ARG; }
+    if ((P->d_fx != nullptr) != (lead->d_fx != nullptr) || (P->d_p8 != nullptr) != (lead->d_p8 != nullptr)) { g_last_error = "bulk coding: streams of one batch must agree on which models are resident"; return CMIXB200_ERR_ARG; }
     if (P->s_fx) CK(cudaStreamSynchronize(P->s_fx));
+    if (P->s_p8) CK(cudaStreamSynchronize(P->s_p8));
     CK(cudaStreamSynchronize(P->s_mix));                 // a lock-step Perceive() may still be in flight
     CK(cudaStreamSynchronize(P->s_small));
     if (!pretrain) TRY(EnsureScratch(P, n_bytes));      // Pretrain() touches models and contexts only: no per-bit scratch
@@ -693,11 +725,11 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
       memset(&a, 0, sizeof a);
       a.st = P->d_st; a.bytes = d_bytes[s] + off;
       a.ext = (d_ext && d_ext[s]) ? d_ext[s] + off * 8 * N_EXT : nullptr;
-      if (P->d_fx) {                                               // resident FXCM: the mixer stages from the generated codes
-        a.fx = P->d_fx;
+      if (P->d_fx || P->d_p8) {                                    // resident FXCM / PAQ8: the mixer stages from the generated codes
+        a.fx = P->d_fx; a.paq8 = P->d_p8;
         a.ext_replay = a.ext;
         if (!pretrain) { a.ext_gen = P->d_ext_gen + off * 8 * N_EXT; a.ext = a.ext_gen; a.lstm_fx = P->d_lstm_fx + off * 8; }
-        any_fx = true;
+        any_fx = any_fx || P->d_fx != nullptr; any_p8 = any_p8 || P->d_p8 != nullptr;
       }
       a.ppmd = (d_ppmd && d_ppmd[s]) ? d_ppmd[s] + off * 256 : nullptr;
       if (!a.ppmd && !pretrain) {                                   // no replay: the resident model produces the distributions
@@ -733,12 +765,13 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
   for (size_t k = 0; k < n_sub; ++k)
     for (int g0 = 0; g0 < n_streams; g0 += gsz) {
       const int cnt = n_streams - g0 < gsz ? n_streams - g0 : gsz;
-      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder, any_ppmd, any_fx));
+      TRY(LaunchChunk(preds[g0], lead->d_args + k * n_streams + g0, cnt, pretrain, any_coder, any_ppmd, any_fx, any_p8));
     }
   for (int g0 = 0; g0 < n_streams; g0 += gsz) {
     cmixb200_predictor* G = preds[g0];
     CK(cudaStreamSynchronize(G->s_small));
     if (any_fx) CK(cudaStreamSynchronize(G->s_fx));
+    if (any_p8) CK(cudaStreamSynchronize(G->s_p8));
     if (!pretrain) {
       if (any_ppmd) CK(cudaStreamSynchronize(G->s_ppmd));
       CK(cudaStreamSynchronize(G->s_lstm));
@@ -764,7 +797,7 @@ const size_t kMaxPiece = 2048;
 int RunPieces(cmixb200_predictor** preds, int n_streams, const u8* const* d_bytes, size_t n_bytes, const u16* const* d_ext,
               const float* const* d_ppmd, float* const* d_p_out, bool pretrain) {
   bool bounded = false;                       // only the codes of resident models need per-bit scratch worth bounding
-  for (int s = 0; s < n_streams; ++s) bounded = bounded || preds[s]->d_fx != nullptr;
+  for (int s = 0; s < n_streams; ++s) bounded = bounded || preds[s]->d_fx != nullptr || preds[s]->d_p8 != nullptr;
   if (pretrain || !bounded || n_bytes <= kMaxPiece) return RunPipelined(preds, n_streams, d_bytes, n_bytes, d_ext, d_ppmd, d_p_out, pretrain);
   std::vector<const u8*> b(n_streams); std::vector<const u16*> e(n_streams); std::vector<const float*> q(n_streams); std::vector<float*> o(n_streams);
   for (size_t off = 0; off < n_bytes; off += kMaxPiece) {
@@ -797,7 +830,6 @@ int cmixb200_create(const uint8_t vocab[256], const char* dictionary_path, int d
 
 int cmixb200_create_ex(const uint8_t vocab[256], const char* dictionary_path, int device, unsigned replay_mask, cmixb200_predictor** out) {
   if (!vocab || !out) { g_last_error = "null argument"; return CMIXB200_ERR_ARG; }
-  replay_mask |= CMIXB200_REPLAY_PAQ8;   // PAQ8 is not resident yet: its 1591 slots are replayed or 0.5
   int n_dev = 0;
   CK(cudaGetDeviceCount(&n_dev));
   if (device < 0 || device >= n_dev) { g_last_error = "no such CUDA device"; return CMIXB200_ERR_CUDA; }
@@ -824,6 +856,7 @@ int cmixb200_create_ex(const uint8_t vocab[256], const char* dictionary_path, in
     cudaStreamCreateWithPriority(&P->s_mix, cudaStreamNonBlocking, p_mix);
     cudaStreamCreateWithPriority(&P->s_ppmd, cudaStreamNonBlocking, p_mix);      // one warp per stream, must never be the one waited for
     cudaStreamCreateWithPriority(&P->s_fx, cudaStreamNonBlocking, p_small);
+    cudaStreamCreateWithPriority(&P->s_p8, cudaStreamNonBlocking, p_small);
     cudaEventCreateWithFlags(&P->ev_lock_mix, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_lock_small, cudaEventDisableTiming);
     cudaEventRecord(P->ev_lock_mix, P->s_mix);
@@ -852,6 +885,7 @@ void cmixb200_destroy(cmixb200_predictor* P) {
   if (P->d_code) cudaFree(P->d_code);
   if (P->s_ppmd) cudaStreamDestroy(P->s_ppmd);
   if (P->s_fx) cudaStreamDestroy(P->s_fx);
+  if (P->s_p8) cudaStreamDestroy(P->s_p8);
   for (int i = 0; i < 8; ++i) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
   if (P->d_ext_gen) cudaFree(P->d_ext_gen);
   if (P->d_lstm_fx) cudaFree(P->d_lstm_fx);
@@ -867,8 +901,9 @@ int cmixb200_feed_external_bit(cmixb200_predictor* P, const uint16_t* codes) {
   CK(cudaSetDevice(P->device));
   CK(cudaStreamSynchronize(P->s_mix));           // the resident models of the previous Perceive() write d_ext_bit on s_mix
   // slots of resident models are produced on the device; only the replayed ones are taken from the caller
-  const size_t first = P->d_fx ? fx::N_OUT : 0;
-  CK(cudaMemcpy(P->d_ext_bit + first, codes + first, (N_EXT - first) * 2, cudaMemcpyHostToDevice));
+  // slots [first, last) are replayed
+  const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? fx::N_OUT : N_EXT;
+  if (last > first) CK(cudaMemcpy(P->d_ext_bit + first, codes + first, (last - first) * 2, cudaMemcpyHostToDevice));
   P->ext_bit_valid = true;
   return CMIXB200_OK;
 }
@@ -890,7 +925,7 @@ float cmixb200_predict(cmixb200_predictor* P) {
   lock_predict_inputs_kernel<<<2, 64, 0, P->s_small>>>(P->d_st, T);
   cudaEventRecord(P->ev_lock_small, P->s_small);
   cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0);
-  mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, (P->ext_bit_valid || P->d_fx) ? P->d_ext_bit : nullptr);
+  mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, (P->ext_bit_valid || P->d_fx || P->d_p8) ? P->d_ext_bit : nullptr);
   mix_predict_final_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T);
   P->launches += 3;
   float p = -1.0f;
@@ -898,8 +933,8 @@ float cmixb200_predict(cmixb200_predictor* P) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
   if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
   if (P->ext_bit_valid) {   // replayed slots fall back to "0.5" until they are fed again
-    const size_t first = P->d_fx ? fx::N_OUT : 0;
-    cudaMemsetAsync(P->d_ext_bit + first, 0xFF, (N_EXT - first) * 2, P->s_mix);
+    const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? fx::N_OUT : N_EXT;
+    if (last > first) cudaMemsetAsync(P->d_ext_bit + first, 0xFF, (last - first) * 2, P->s_mix);
   }
   P->ext_bit_valid = false;
   return p;
@@ -926,6 +961,7 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
   // FXCM is perceived last and sees the LSTM's read-out of the next bit (predictor.cpp:462-466)
   if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 0, P->d_ext_bit); P->launches++; }
+  if (P->d_p8) { paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), P->s_mix>>>(P->d_p8, bit, P->d_ext_bit); P->launches++; }
   CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
   P->launches += 2;
   CK(cudaGetLastError());
@@ -944,6 +980,7 @@ int cmixb200_pretrain(cmixb200_predictor* P, int bit) {
   small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, nullptr, 1);
   P->launches += 2;
   if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 1, P->d_ext_bit); P->launches++; }
+  if (P->d_p8) { paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), P->s_mix>>>(P->d_p8, bit, P->d_ext_bit); P->launches++; }
   CK(cudaGetLastError());
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   return CMIXB200_OK;
@@ -1084,6 +1121,7 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
   CK(cudaStreamSynchronize(P->s_mix));
   CK(cudaStreamSynchronize(P->s_small));
   if (P->s_fx) CK(cudaStreamSynchronize(P->s_fx));
+  if (P->s_p8) CK(cudaStreamSynchronize(P->s_p8));
   const void* src = nullptr;
   switch (what) {
     case CMIXB200_DBG_SMALL_X: src = P->d_small_x; break;

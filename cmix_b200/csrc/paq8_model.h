@@ -262,54 +262,92 @@ P8_HD inline void cm_set(Cm& m, u64 cx) {
   m.chk[m.cn] = (u16)(checksum64(cx, m.hashbits, 16) & 0xffff);
   m.cn++;
 }
-// ContextMap::mix1 (:1069-1145). `rnd` is the global generator: draws happen in context order.
-P8_HD inline int cm_mix(Cm& m, Out& o, Rnd& rnd, int y, int c0, int bp, int c1) {
-  const Tables& T = *o.T;
-  u8* t = m.t;
-  int result = 0;
-  for (int i = 0; i < m.cn; ++i) {
-    if (m.cp[i] != P8_NULL) {
-      int ns = T.state[t[m.cp[i]]][y];
-      if (ns >= 204 && (u32)(rnd_next(rnd) << ((452 - ns) >> 3))) ns -= 4;
-      t[m.cp[i]] = (u8)ns;
-    }
-    if (bp > 1 && t[m.runp[i]] == 0) m.cp[i] = P8_NULL;
-    else {
-      switch (bp) {
-        case 1: case 3: case 6: m.cp[i] = m.cp0[i] + 1 + (c0 & 1); break;
-        case 4: case 7: m.cp[i] = m.cp0[i] + 3 + (c0 & 3); break;
-        case 2: case 5: m.cp0[i] = m.cp[i] = bucket_find(t, (m.cxt[i] + (u32)c0) & m.mask, m.chk[i]); break;
-        default: {
-          m.cp0[i] = m.cp[i] = bucket_find(t, (m.cxt[i] + (u32)c0) & m.mask, m.chk[i]);
-          if (t[m.cp0[i] + 3] == 2) deferred_histories(t, m.mask, m.cxt[i], m.chk[i], m.cp0[i]);
-          u8* rp = t + m.runp[i];
-          if (rp[0] == 0) { rp[0] = 2; rp[1] = (u8)c1; }
-          else if (rp[1] != c1) { rp[0] = 1; rp[1] = (u8)c1; }
-          else if (rp[0] < 254) rp[0] += 2;
-          else if (rp[0] == 255) rp[0] = 128;
-          m.runp[i] = m.cp0[i] + 3;
-        } break;
+// ---- ContextMap::mix1 (:1069-1145) cut per context, so that a CTA can run the contexts of a map side by side when they touch
+// disjoint buckets this bit (paq8.cuh) and fall back to the in-order loop (cm_mix) when they do not.
+// cm_next_state: the aged bit-history state context i would store this bit, BEFORE the random down-step (read-only); -1 = no cell.
+P8_HD inline int cm_next_state(const Tables& T, const Cm& m, int i, int y) { return m.cp[i] != P8_NULL ? T.state[m.t[m.cp[i]]][y] : -1; }
+P8_HD inline bool cm_draw_hits(u32 r, int ns) { return (u32)(r << ((452 - ns) >> 3)) != 0; }   // `rnd() << ((452-ns)>>3)` (:1075)
+// Read-only probe: which slot of `bucket` holds checksum ch (-1 = none: find would replace).
+P8_HD inline int bucket_peek(const u8* t, u32 bucket, u16 ch) {
+  const u8* e = t + ((size_t)bucket << 6);
+  const u16* chk = reinterpret_cast<const u16*>(e);
+  const u8 last = e[14];
+  if (chk[last & 15] == ch) return last & 15;
+  for (int i = 0; i < 7; ++i) if (chk[i] == ch) return i;
+  return -1;
+}
+// The buckets context i reads or writes this bit (at most 5): its live cell bucket, its run-info bucket, the bucket it moves to and,
+// on a byte boundary, the two buckets of a deferred history write-back. Returns how many ids were stored.
+P8_HD inline int touched_buckets(const u8* t, u32 mask, int cell, int run, u32 ctx, u16 chk, u32 add, int bp, u32* ids) {
+  int n = 0;
+  if (cell != P8_NULL) ids[n++] = (u32)cell >> 6;
+  ids[n++] = (u32)run >> 6;
+  if (bp > 1 && t[run] == 0) return n;
+  if (bp == 0 || bp == 2 || bp == 5) {
+    const u32 b = (ctx + add) & mask;
+    ids[n++] = b;
+    if (bp == 0) {
+      const int slot = bucket_peek(t, b, chk);
+      if (slot >= 0) {
+        const u8* cell0 = t + ((size_t)b << 6) + 15 + 7 * slot;
+        if (cell0[3] == 2) { const int c = cell0[4] + 256; ids[n++] = (ctx + (u32)(c >> 6)) & mask; ids[n++] = (ctx + (u32)(c >> 3)) & mask; }
       }
     }
-    const u8* rp = t + m.runp[i];
-    const int rc = rp[0];
-    if (((rp[1] + 256) >> (8 - bp)) == c0) {
-      const int b = ((rp[1] >> (7 - bp)) & 1) * 2 - 1;
-      const int c = ilog(T, rc + 1) << (2 + (~rc & 1));
-      add(o, b * c);
-    } else add(o, 0);
-    const int s = m.cp[i] != P8_NULL ? t[m.cp[i]] : 0;
-    Sm16 smi; smi.t = m.sm_t + i * 256; smi.cxt = m.sm_cxt[i];
-    const int p1 = sm16_p(smi, y, s);
-    m.sm_cxt[i] = smi.cxt;
-    const int st = (stretch(T, p1) + 2) >> 2;
-    add(o, st);
-    add(o, (p1 - 2047 + 4) >> 3);
-    const int n0 = -!T.state[s][2], n1 = -!T.state[s][3];
-    add(o, st * iabs(n1 - n0));
-    const int p0 = 4095 - p1;
-    add(o, ((p1 & n0) - (p0 & n1) + 8) >> 4);
-    result += s > 0;
+  }
+  return n;
+}
+P8_HD inline int cm_touched(const Cm& m, int i, int c0, int bp, u32* ids) { return touched_buckets(m.t, m.mask, m.cp[i], m.runp[i], m.cxt[i], m.chk[i], (u32)c0, bp, ids); }
+// One context of one bit: store the aged state `ns` (already decided, -1 = no cell), move to the next cell, emit 5 inputs at o.
+P8_HD inline int cm_step(Cm& m, int i, Out& o, int ns, int y, int c0, int bp, int c1) {
+  const Tables& T = *o.T;
+  u8* t = m.t;
+  if (m.cp[i] != P8_NULL) t[m.cp[i]] = (u8)ns;
+  if (bp > 1 && t[m.runp[i]] == 0) m.cp[i] = P8_NULL;
+  else {
+    switch (bp) {
+      case 1: case 3: case 6: m.cp[i] = m.cp0[i] + 1 + (c0 & 1); break;
+      case 4: case 7: m.cp[i] = m.cp0[i] + 3 + (c0 & 3); break;
+      case 2: case 5: m.cp0[i] = m.cp[i] = bucket_find(t, (m.cxt[i] + (u32)c0) & m.mask, m.chk[i]); break;
+      default: {
+        m.cp0[i] = m.cp[i] = bucket_find(t, (m.cxt[i] + (u32)c0) & m.mask, m.chk[i]);
+        if (t[m.cp0[i] + 3] == 2) deferred_histories(t, m.mask, m.cxt[i], m.chk[i], m.cp0[i]);
+        u8* rp = t + m.runp[i];
+        if (rp[0] == 0) { rp[0] = 2; rp[1] = (u8)c1; }
+        else if (rp[1] != c1) { rp[0] = 1; rp[1] = (u8)c1; }
+        else if (rp[0] < 254) rp[0] += 2;
+        else if (rp[0] == 255) rp[0] = 128;
+        m.runp[i] = m.cp0[i] + 3;
+      } break;
+    }
+  }
+  const u8* rp = t + m.runp[i];
+  const int rc = rp[0];
+  if (((rp[1] + 256) >> (8 - bp)) == c0) {
+    const int b = ((rp[1] >> (7 - bp)) & 1) * 2 - 1;
+    const int c = ilog(T, rc + 1) << (2 + (~rc & 1));
+    add(o, b * c);
+  } else add(o, 0);
+  const int s = m.cp[i] != P8_NULL ? t[m.cp[i]] : 0;
+  Sm16 smi; smi.t = m.sm_t + i * 256; smi.cxt = m.sm_cxt[i];
+  const int p1 = sm16_p(smi, y, s);
+  m.sm_cxt[i] = smi.cxt;
+  const int st = (stretch(T, p1) + 2) >> 2;
+  add(o, st);
+  add(o, (p1 - 2047 + 4) >> 3);
+  const int n0 = -!T.state[s][2], n1 = -!T.state[s][3];
+  add(o, st * iabs(n1 - n0));
+  const int p0 = 4095 - p1;
+  add(o, ((p1 & n0) - (p0 & n1) + 8) >> 4);
+  return s > 0;
+}
+// The in-order loop. `rnd` is the global generator: draws happen in context order.
+P8_HD inline int cm_mix(Cm& m, Out& o, Rnd& rnd, int y, int c0, int bp, int c1) {
+  const Tables& T = *o.T;
+  int result = 0;
+  for (int i = 0; i < m.cn; ++i) {
+    int ns = cm_next_state(T, m, i, y);
+    if (ns >= 204 && cm_draw_hits(rnd_next(rnd), ns)) ns -= 4;
+    result += cm_step(m, i, o, ns, y, c0, bp, c1);
   }
   if (bp == 7) m.cn = 0;
   return result;
@@ -321,15 +359,86 @@ P8_HD inline void cm2_set(Cm2& m, u64 ctx) {
   m.chk[m.index] = (u16)(checksum64(ctx, m.hashbits, 16) & 0xffff);
   m.index++;
 }
-// ContextMap2::mix (:1294-1358) including Update (:1204-1260)
-P8_HD inline int cm2_mix(Cm2& m, Out& o, int y, int bpos) {
-  const Tables& T = *o.T;
-  u8* t = m.t;
+// ---- ContextMap2::mix (:1294-1358) including Update (:1204-1260), cut into prologue / per-context step / epilogue
+P8_HD inline void cm2_begin(Cm2& m, int y, int bpos) {
   m.last_bit = (u8)y;
   m.bit_pos = (u8)bpos;
   m.bits += m.bits + (u32)y;
   m.last_byte = (u8)(m.bits & 0xFF);
   if (bpos == 0) m.bits = 1;
+}
+P8_HD inline int cm2_touched(const Cm2& m, int i, int bp, u32* ids) { return touched_buckets(m.t, m.mask, m.bs[i], m.bh[i], m.cxt[i], m.chk[i], m.bits, bp, ids); }
+P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
+  const Tables& T = *o.T;
+  u8* t = m.t;
+  if (m.bs[i] != P8_NULL) t[m.bs[i]] = T.state[t[m.bs[i]]][y];
+  if (bpos > 1 && t[m.bh[i]] == 0) m.bs[i] = P8_NULL;
+  else {
+    switch (bpos) {
+      case 0: {
+        m.bs[i] = m.bs0[i] = bucket_find(t, (m.cxt[i] + m.bits) & m.mask, m.chk[i]);
+        if (t[m.bs0[i] + 3] == 2) deferred_histories(t, m.mask, m.cxt[i], m.chk[i], m.bs0[i]);
+        u8* h = t + m.bh[i];
+        h[3] = h[2];
+        h[2] = h[1];
+        if (h[0] == 0) { h[0] = 2; h[1] = m.last_byte; }
+        else if (h[1] != m.last_byte) { h[0] = 1; h[1] = m.last_byte; }
+        else if (h[0] < 254) h[0] += 2;
+        else if (h[0] == 255) h[0] = 128;
+        m.bh[i] = m.bs0[i] + 3;
+        m.has_history[i] = t[m.bs0[i]] > 15;
+        break;
+      }
+      case 2: case 5: m.bs[i] = m.bs0[i] = bucket_find(t, (m.cxt[i] + m.bits) & m.mask, m.chk[i]); break;
+      case 1: case 3: case 6: m.bs[i] = m.bs0[i] + 1 + y; break;
+      case 4: case 7: m.bs[i] = m.bs0[i] + 3 + (int)(m.bits & 3); break;
+    }
+  }
+  int state = m.bs[i] != P8_NULL ? t[m.bs[i]] : 0;
+  const int result = state > 0;
+  Sm32 q; q.n = 0;
+  q.t = m.m8_t + i * 256; q.cxt = m.m8_cxt[i];
+  int p1 = sm32_p(T, q, y, state);
+  m.m8_cxt[i] = q.cxt;
+  int n0 = T.state[state][2], n1 = T.state[state][3], k = -~n1;
+  k = (k * 64) / (k - ~n0);
+  n0 = -!n0; n1 = -!n1;
+  const u8* h = t + m.bh[i];
+  if ((u32)((h[1] + 256) >> (8 - bpos)) == m.bits) {
+    const int rs = h[0];
+    const int sign = ((h[1] >> (7 - bpos)) & 1) * 2 - 1;
+    add(o, sign * (ilog(T, rs + 1) << (3 - (rs & 1))));
+  } else if (bpos > 0 && (h[0] & 1) > 0) {
+    if ((u32)((h[2] + 256) >> (8 - bpos)) == m.bits) add(o, (((h[2] >> (7 - bpos)) & 1) * 2 - 1) * 128);
+    else if (m.has_history[i] && (u32)((h[3] + 256) >> (8 - bpos)) == m.bits) add(o, (((h[3] >> (7 - bpos)) & 1) * 2 - 1) * 128);
+    else add(o, 0);
+  } else add(o, 0);
+  if (m.has_history[i]) {
+    state = (h[1] >> (7 - bpos)) & 1;
+    state |= ((h[2] >> (7 - bpos)) & 1) * 2;
+    state |= ((h[3] >> (7 - bpos)) & 1) * 4;
+  } else state = 8;
+  const int st = stretch(T, p1) >> 2;
+  add(o, st);
+  add(o, (p1 - 2047) >> 3);
+  p1 >>= 4;
+  const int p0 = 255 - p1;
+  add(o, st * iabs(n1 - n0));
+  add(o, (p1 & n0) - (p0 & n1));
+  q.t = m.m12_t + i * 4608; q.cxt = m.m12_cxt[i];
+  add(o, stretch(T, sm32_p(T, q, y, (state << 9) | (bpos << 6) | k)) >> 2);
+  m.m12_cxt[i] = q.cxt;
+  q.t = m.m6_t + i * 72; q.cxt = m.m6_cxt[i];
+  add(o, stretch(T, sm32_p(T, q, y, (state << 3) | bpos)) >> 2);
+  m.m6_cxt[i] = q.cxt;
+  return result;
+}
+// In-order evaluation. The reference updates ALL contexts before predicting from any (two loops); the per-context fusion
+// below is the same computation whenever the contexts touch disjoint buckets this bit, and the two-loop order otherwise.
+P8_HD inline int cm2_mix_body(Cm2& m, Out& o, int y, int bpos) {   // after cm2_begin(), before the byte-end reset of `index`
+  const Tables& T = *o.T;
+  u8* t = m.t;
+  // loop 1 (Update): cells and pointers only
   for (int i = 0; i < m.index; ++i) {
     if (m.bs[i] != P8_NULL) t[m.bs[i]] = T.state[t[m.bs[i]]][y];
     if (bpos > 1 && t[m.bh[i]] == 0) m.bs[i] = P8_NULL;
@@ -355,6 +464,7 @@ P8_HD inline int cm2_mix(Cm2& m, Out& o, int y, int bpos) {
       }
     }
   }
+  // loop 2: predictions
   int result = 0;
   for (int i = 0; i < m.index; ++i) {
     int state = m.bs[i] != P8_NULL ? t[m.bs[i]] : 0;
@@ -395,6 +505,11 @@ P8_HD inline int cm2_mix(Cm2& m, Out& o, int y, int bpos) {
     add(o, stretch(T, sm32_p(T, q, y, (state << 3) | bpos)) >> 2);
     m.m6_cxt[i] = q.cxt;
   }
+  return result;
+}
+P8_HD inline int cm2_mix(Cm2& m, Out& o, int y, int bpos) {
+  cm2_begin(m, y, bpos);
+  const int result = cm2_mix_body(m, o, y, bpos);
   if (bpos == 7) m.index = 0;
   return result;
 }

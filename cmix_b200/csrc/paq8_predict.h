@@ -202,7 +202,7 @@ P8_HD inline void match_bit(State& S, Out& o) {
 }
 
 // ---------------------------------------------------------------- sparse match model (:3694-3843)
-P8_HD inline void smatch_bit(State& S, Out& o) {
+P8_HD inline void smatch_core(State& S, Out& o) {
   SparseMatchM& M = S.smatch;
   const u32 offset_[4] = {0, 1, 0, 0}, stride_[4] = {1, 1, 2, 1}, minlen_[4] = {5, 4, 4, 5}, bitmask_[4] = {0xDF, 0xFF, 0xDF, 0x0F};
   const int y = S.y, bpos = S.bpos, c0 = S.c0;
@@ -266,6 +266,10 @@ P8_HD inline void smatch_bit(State& S, Out& o) {
     } else { add(o, 0); add(o, 0); add(o, 0); }
     for (int i = 0; i < 4; ++i) stm_mix(M.maps[i], o, y, 1, 2);
   } else for (int i = 0; i < 11; ++i) add(o, 0);
+}
+P8_HD inline void smatch_select(State& S) {   // the model's two mixer selector sets (:3839-3840)
+  const SparseMatchM& M = S.smatch;
+  const int bpos = S.bpos, c0 = S.c0;
   mset(S.m, (int)((M.hash_index << 6) | ((u32)bpos << 3) | umin(7, M.length)), 4 * 64);
   mset(S.m, (int)((M.hash_index << 11) | (umin(7, ilog2(M.length + 1)) << 8) | (u32)(c0 ^ (M.expected >> (8 - bpos)))), 4 * 2048);
 }
@@ -494,37 +498,49 @@ P8_HD inline void record_byte(State& S) {
   M.wpos1[w] = pos;
   M.mx_ctx = (rl > 128) ? imin(0x7F, col / imax(1, rl / 128)) : col;
 }
-P8_HD inline void record_bit(State& S, Out& o, Rnd& rnd) {
+P8_HD inline void record_pre(State& S) {   // per-bit context selection of the direct maps (:4412-4418)
   RecordM& M = S.record;
-  const int y = S.y, bpos = S.bpos, c0 = S.c0;
-  const int c1 = buf(S, 1);
-  if (bpos == 0) record_byte(S);
-  const u8 B = (u8)(c0 << (8 - bpos));
+  const int bpos = S.bpos;
+  const u8 B = (u8)(S.c0 << (8 - bpos));
   const u32 ctx = (u32)(M.N ^ B) | ((u32)bpos << 8);
-  ictx_push(M.ictx[4], (u32)y); ictx_select(M.ictx[4], ctx);
+  ictx_push(M.ictx[4], (u32)S.y); ictx_select(M.ictx[4], ctx);
   stm_set_direct(M.maps[5], ctx);
   scm_set(M.smap[0], ctx);
   scm_set(M.smap[1], ictx_get(M.ictx[4]));
   scm_set(M.smap[2], (ctx << 8) | M.WxNW);
-  cm_mix(M.cm, o, rnd, y, c0, bpos, c1);
-  cm_mix(M.cn, o, rnd, y, c0, bpos, c1);
-  cm_mix(M.co, o, rnd, y, c0, bpos, c1);
-  cm_mix(M.cp, o, rnd, y, c0, bpos, c1);
-  for (int i = 0; i < 6; ++i) stm_mix(M.maps[i], o, y, 1, 3);
-  for (int i = 0; i < 3; ++i) imap_mix(M.imap[i], o, y, 1, 3, 255);
-  scm_mix(M.smap[0], o, y, 6, 1, 3);
-  scm_mix(M.smap[1], o, y, 6, 1, 3);
-  scm_mix(M.smap[2], o, y, 5, 1, 2);
+}
+P8_HD inline void record_small(State& S, Out& o, int k) {   // the 12 direct maps behind the four context maps, k = 0..11
+  RecordM& M = S.record;
+  const int y = S.y;
+  if (k < 6) stm_mix(M.maps[k], o, y, 1, 3);
+  else if (k < 9) imap_mix(M.imap[k - 6], o, y, 1, 3, 255);
+  else if (k < 11) scm_mix(M.smap[k - 9], o, y, 6, 1, 3);
+  else scm_mix(M.smap[2], o, y, 5, 1, 2);
+}
+P8_HD inline void record_select(State& S) {   // selector sets and ModelStats (:4429-4433)
+  RecordM& M = S.record;
+  const int bpos = S.bpos;
+  const u8 B = (u8)(S.c0 << (8 - bpos));
   mset(S.m, (M.rlen[0] > 2) * ((bpos << 7) | M.mx_ctx), 1024);
   mset(S.m, ((M.N ^ B) >> 4) | (M.x << 4), 512);
   mset(S.m, (S.grp0 << 5) | M.x, 11 * 32);
   S.st_record = ((u32)imin(0xFFFF, M.rlen[0]) << 16) | (u32)imin(0xFFFF, M.col);
 }
-P8_HD inline void record1_bit(State& S, Out& o, Rnd& rnd) {
+P8_HD inline void record_core(State& S, Out& o, Rnd& rnd) {
+  RecordM& M = S.record;
+  const int y = S.y, bpos = S.bpos, c0 = S.c0;
+  const int c1 = buf(S, 1);
+  if (bpos == 0) record_byte(S);
+  record_pre(S);
+  cm_mix(M.cm, o, rnd, y, c0, bpos, c1);
+  cm_mix(M.cn, o, rnd, y, c0, bpos, c1);
+  cm_mix(M.co, o, rnd, y, c0, bpos, c1);
+  cm_mix(M.cp, o, rnd, y, c0, bpos, c1);
+  for (int k = 0; k < 12; ++k) record_small(S, o, k);
+}
+P8_HD inline void record1_byte(State& S) {
   const Tables& T = *S.T;
   Record1M& M = S.record1;
-  const int y = S.y, bpos = S.bpos, c0 = S.c0, c1 = buf(S, 1);
-  if (bpos == 0) {
     const u32 c4 = S.c4;
     const int w = (int)(c4 & 0xffff), c = w & 255, d = w & 0xf0ff, e = (int)(c4 & 0xffffff), pos = S.pos;
     cm_set(M.cm, sx(c << 8 | (imin(255, pos - M.cpos1[c]) / 4)));
@@ -547,7 +563,11 @@ P8_HD inline void record1_bit(State& S, Out& o, Rnd& rnd) {
     cm_set(M.cq, sx(e));
     M.cpos1[c] = pos;
     M.wpos1[w] = pos;
-  }
+}
+P8_HD inline void record1_bit(State& S, Out& o, Rnd& rnd) {
+  Record1M& M = S.record1;
+  const int y = S.y, bpos = S.bpos, c0 = S.c0, c1 = buf(S, 1);
+  if (bpos == 0) record1_byte(S);
   cm_mix(M.cm, o, rnd, y, c0, bpos, c1);
   cm_mix(M.cn, o, rnd, y, c0, bpos, c1);
   cm_mix(M.co, o, rnd, y, c0, bpos, c1);
@@ -1010,14 +1030,17 @@ P8_HD inline void xml_byte(State& S) {
   cm_set(M.cm, hash(++i, pTag->name, sx(M.state * 2 + pTag->end_tag), pTag->c_type, Tag->c_type));
   cm_set(M.cm, hash(++i, sx(M.state * 2 + Tag->end_tag), Tag->name, Tag->c_type, (u64)(c4 & 0xE0FF)));
 }
-P8_HD inline void xml_bit(State& S, Out& o, Rnd& rnd) {
+P8_HD inline void xml_stats(State& S) {
   XmlM& M = S.xml;
-  if (S.bpos == 0) xml_byte(S);
-  cm_mix(M.cm, o, rnd, S.y, S.c0, S.bpos, buf(S, 1));
   const int bpos = S.bpos;
   const u32 bh = M.state_bh[M.state];
   const u8 s = (u8)(((bh >> (28 - bpos)) & 0x08) | ((bh >> (21 - bpos)) & 0x04) | ((bh >> (14 - bpos)) & 0x02) | ((bh >> (7 - bpos)) & 0x01) | (bpos << 4));
   S.st_xml = ((u32)s << 3) | (u32)M.state;
+}
+P8_HD inline void xml_bit(State& S, Out& o, Rnd& rnd) {
+  if (S.bpos == 0) xml_byte(S);
+  cm_mix(S.xml.cm, o, rnd, S.y, S.c0, S.bpos, buf(S, 1));
+  xml_stats(S);
 }
 
 }  // namespace p8

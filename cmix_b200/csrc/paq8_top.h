@@ -286,6 +286,7 @@ P8_HD inline void text_contexts(State& S) {
   cm2_set(map, hash((M.ascii_mask >> 15) & ((1 << 30) - 1), (u64)buf(S, 1), (u64)buf(S, 2), (u64)buf(S, 3)));
 }
 
+P8_HD inline void text_select(State& S);
 P8_HD inline void text_bit(State& S, Out& o) {
   TextM& M = S.text;
   if (S.bpos == 0) {
@@ -293,6 +294,10 @@ P8_HD inline void text_bit(State& S, Out& o) {
     text_contexts(S);
   }
   cm2_mix(M.map, o, S.y, S.bpos);
+  text_select(S);
+}
+P8_HD inline void text_select(State& S) {   // the model's eight mixer selector sets (:3166-3185)
+  TextM& M = S.text;
   const int c0 = S.c0;
   const u32 wl0 = M.word_length[0], wl1 = M.word_length[1], gap = M.word_gap;
   const Word& pw = P8_PW;
@@ -539,10 +544,15 @@ P8_HD inline void exe_byte(State& S) {
   cm2_set(cm, hash(sx(++i), (u64)((0x100 | B) * (op.bytes_read > 0)), sx(st + 16 * M.pstate + 256 * op.bytes_read),
                    (u64)(((op.flags & fMODE) == fAM) * 16 + (op.rex & 0x08) + (op.o16) * 4 + ((op.code & 0xFE) == 0xE8) * 2 + ((op.data & X_MultiByteOpcode) != 0 && (op.code & 0xF0) == 0x80))));
 }
+P8_HD inline void exe_select(State& S);
 P8_HD inline void exe_bit(State& S, Out& o) {
   ExeM& M = S.exe;
   if (S.bpos == 0) exe_byte(S);
   cm2_mix(M.cm, o, S.y, S.bpos);
+  exe_select(S);
+}
+P8_HD inline void exe_select(State& S) {   // selector sets and ModelStats (:7526-7545)
+  ExeM& M = S.exe;
   const int bpos = S.bpos, c0 = S.c0, st = M.state;
   const Instr& op = M.op;
   const u32 bh = M.state_bh[M.context];
@@ -614,12 +624,10 @@ P8_HD inline void ols_update(double* blk, int& km, u8 val) {
     km = 0;
   }
 }
-P8_HD inline void linear_bit(State& S, Out& o) {
+P8_HD inline void linear_predict(State& S) {   // Add() the new taps and Predict() (after the three Update() calls)
   LinearM& M = S.linear;
-  const int bpos = S.bpos;
-  if (bpos == 0) {
+  {
     const u8 W = (u8)buf(S, 1), WW = (u8)buf(S, 2), WWW = (u8)buf(S, 3);
-    for (int k = 0; k < 3; ++k) ols_update(M.ols + (size_t)k * OLS_STRIDE, M.ols_km[k], W);
     for (int i = 1; i <= 32; ++i) {
       const int idx[3] = {i, i * 2 - 1, i * 2};
       for (int k = 0; k < 3; ++k) if (M.ols_index[k] < OLS_N) M.ols[(size_t)k * OLS_STRIDE + M.ols_index[k]++] = (double)(u8)buf(S, idx[k]);
@@ -636,11 +644,21 @@ P8_HD inline void linear_bit(State& S, Out& o) {
     M.prd[3] = (u8)clip8(W * 2 - WW);
     M.prd[4] = (u8)clip8(W * 3 - WW * 3 + WWW);
   }
-  const u8 B = (u8)(S.c0 << (8 - bpos));
-  for (int i = 0; i < 5; ++i) {
-    scm_set(M.smap[i], (u32)((M.prd[i] - B) * 8 + bpos));
-    scm_mix(M.smap[i], o, S.y, 6, 1, 2);
+}
+P8_HD inline void linear_small(State& S, Out& o, int i) {
+  LinearM& M = S.linear;
+  const u8 B = (u8)(S.c0 << (8 - S.bpos));
+  scm_set(M.smap[i], (u32)((M.prd[i] - B) * 8 + S.bpos));
+  scm_mix(M.smap[i], o, S.y, 6, 1, 2);
+}
+P8_HD inline void linear_bit(State& S, Out& o) {
+  LinearM& M = S.linear;
+  if (S.bpos == 0) {
+    const u8 W = (u8)buf(S, 1);
+    for (int k = 0; k < 3; ++k) ols_update(M.ols + (size_t)k * OLS_STRIDE, M.ols_km[k], W);
+    linear_predict(S);
   }
+  for (int i = 0; i < 5; ++i) linear_small(S, o, i);
 }
 
 // ---------------------------------------------------------------- header detectors in front of the unmodelled image / audio / JPEG paths
@@ -706,77 +724,42 @@ P8_HD inline int mixer_predict(const Tables& T, Mixer& m, int y, u16* codes) {  
   return m.pr2 = squash(T, z >> 9);
 }
 
-P8_HD inline int context_model(State& S) {
-  const Tables& T = *S.T;
-  const int y = S.y, bpos = S.bpos;
-  if (bpos == 0) {
-    --S.size;
-    ++S.blpos;
-    if (S.size == -1) { S.info = 0; S.ft2 = buf(S, 1); }
-    if (S.size == -5 && !(S.ft2 == FT_TEXT || S.ft2 == FT_IMAGE1 || S.ft2 == FT_IMAGE4 || S.ft2 == FT_IMAGE8 || S.ft2 == FT_IMAGE8GRAY || S.ft2 == FT_IMAGE24 || S.ft2 == FT_IMAGE32)) {
-      S.size = buf(S, 4) << 24 | buf(S, 3) << 16 | buf(S, 2) << 8 | buf(S, 1);
-      S.blpos = 0;
-    }
-    if (S.size == -9) {
-      S.size = buf(S, 8) << 24 | buf(S, 7) << 16 | buf(S, 6) << 8 | buf(S, 5);
-      S.info = buf(S, 4) << 24 | buf(S, 3) << 16 | buf(S, 2) << 8 | buf(S, 1);
-      S.blpos = 0;
-      if (S.ft2 == FT_TEXT && S.info) S.size = S.info - 8;
-    }
-    if (!S.blpos) S.filetype = S.ft2;
-    if (S.size == 0) S.filetype = FT_DEFAULT;
-    S.st_type = S.filetype;
-    if (S.filetype == FT_JPEG || (S.filetype >= FT_IMAGE1 && S.filetype <= FT_AUDIO)) S.error |= ERR_UNSUPPORTED_BLOCK;
-    detect_byte(S);
+// block header parsing in front of contextModel2 (:8116-8134): filetype and bytes remaining of the current block
+P8_HD inline void block_parse(State& S) {
+  --S.size;
+  ++S.blpos;
+  if (S.size == -1) { S.info = 0; S.ft2 = buf(S, 1); }
+  if (S.size == -5 && !(S.ft2 == FT_TEXT || S.ft2 == FT_IMAGE1 || S.ft2 == FT_IMAGE4 || S.ft2 == FT_IMAGE8 || S.ft2 == FT_IMAGE8GRAY || S.ft2 == FT_IMAGE24 || S.ft2 == FT_IMAGE32)) {
+    S.size = buf(S, 4) << 24 | buf(S, 3) << 16 | buf(S, 2) << 8 | buf(S, 1);
+    S.blpos = 0;
   }
+  if (S.size == -9) {
+    S.size = buf(S, 8) << 24 | buf(S, 7) << 16 | buf(S, 6) << 8 | buf(S, 5);
+    S.info = buf(S, 4) << 24 | buf(S, 3) << 16 | buf(S, 2) << 8 | buf(S, 1);
+    S.blpos = 0;
+    if (S.ft2 == FT_TEXT && S.info) S.size = S.info - 8;
+  }
+  if (!S.blpos) S.filetype = S.ft2;
+  if (S.size == 0) S.filetype = FT_DEFAULT;
+  S.st_type = S.filetype;
+  if (S.filetype == FT_JPEG || (S.filetype >= FT_IMAGE1 && S.filetype <= FT_AUDIO)) S.error |= ERR_UNSUPPORTED_BLOCK;
+  detect_byte(S);
+}
+P8_HD inline void ordern_byte(State& S) {   // :8140-8152
+  const u8 B = (u8)S.c4;
+  S.cxt[15] = is_alpha(B) ? (u32)combine64(S.cxt[15], (u64)lower(B)) : 0;
+  cm2_set(S.cm, S.cxt[15]);
+  for (int i = 14; i > 0; --i) S.cxt[i] = (u32)combine64(S.cxt[i - 1], B);
+  for (int i = 0; i < 7; ++i) cm2_set(S.cm, S.cxt[i]);
+  rcm_set(S.rcm7, S.cxt[7], buf(S, 1));
+  cm2_set(S.cm, S.cxt[8]);
+  rcm_set(S.rcm9, S.cxt[10], buf(S, 1));
+  rcm_set(S.rcm10, S.cxt[12], buf(S, 1));
+  cm2_set(S.cm, S.cxt[14]);
+}
+P8_HD inline void main_select(State& S, int order) {   // the nine selector sets of contextModel2 itself (:8187-8202)
   Mixer& m = S.m;
-  mixer_train(m, y);
-  Out o; o.T = &T; o.tx = m.tx; o.codes = S.codes; o.n = 0;
-  add(o, 64);
-  const int c0 = S.c0;
-  if (bpos == 0) {
-    const u8 B = (u8)S.c4;
-    S.cxt[15] = is_alpha(B) ? (u32)combine64(S.cxt[15], (u64)lower(B)) : 0;
-    cm2_set(S.cm, S.cxt[15]);
-    for (int i = 14; i > 0; --i) S.cxt[i] = (u32)combine64(S.cxt[i - 1], B);
-    for (int i = 0; i < 7; ++i) cm2_set(S.cm, S.cxt[i]);
-    rcm_set(S.rcm7, S.cxt[7], buf(S, 1));
-    cm2_set(S.cm, S.cxt[8]);
-    rcm_set(S.rcm9, S.cxt[10], buf(S, 1));
-    rcm_set(S.rcm10, S.cxt[12], buf(S, 1));
-    cm2_set(S.cm, S.cxt[14]);
-  }
-  add(o, (stretch(T, sm32_p(T, S.sm0, y, c0)) + 1) >> 1);
-  add(o, (stretch(T, sm32_p(T, S.sm1, y, c0 | (buf(S, 1) << 8))) + 1) >> 1);
-  int order = cm2_mix(S.cm, o, y, bpos);
-  rcm_mix(S.rcm7, o, c0, bpos);
-  rcm_mix(S.rcm9, o, c0, bpos);
-  rcm_mix(S.rcm10, o, c0, bpos);
-  match_bit(S, o);
-  const int ismatch = ilog(T, S.match.length);
-  smatch_bit(S, o);
-  if (bpos == 0) { sparse_byte(S, ismatch, order); }
-  cm_mix(S.sparse.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  if (bpos == 0) sparse1_byte(S, ismatch, order);
-  cm_mix(S.sparse1.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  for (int k = 0; k < 7; ++k) scm_mix(S.sparse1.scm[k], o, y);
-  if (bpos == 0) distance_byte(S);
-  cm_mix(S.distance.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  pic_bit(S, o);
-  record_bit(S, o, S.rnd);
-  record1_bit(S, o, S.rnd);
-  if (bpos == 0) word_byte(S);
-  cm_mix(S.word.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  if (bpos == 0) nest_byte(S);
-  cm_mix(S.nest.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  if (bpos == 0) indirect_byte(S);
-  cm_mix(S.indirect.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
-  dmc_bit(S, o);
-  xml_bit(S, o, S.rnd);
-  text_bit(S, o);
-  exe_bit(S, o);
-  linear_bit(S, o);
-  m.nx = o.n;
+  const int bpos = S.bpos, c0 = S.c0;
   mset(m, (imax(0, order - 3) << 3) | bpos, 64);
   order = imax(0, order - 5);
   const u32 d = (u32)c0 << (8 - bpos);
@@ -791,11 +774,57 @@ P8_HD inline int context_model(State& S) {
   mset(m, (int)((u32)bpos * 256 + (((S.words << bpos & 255) >> bpos) | (d & 255))), 2048);
   mset(m, S.last_prediction / 16, 256);
   mset(m, c0, 256);
+}
+
+P8_HD inline int context_model(State& S) {
+  const Tables& T = *S.T;
+  const int y = S.y, bpos = S.bpos;
+  if (bpos == 0) block_parse(S);
+  Mixer& m = S.m;
+  mixer_train(m, y);
+  Out o; o.T = &T; o.tx = m.tx; o.codes = S.codes; o.n = 0;
+  add(o, 64);
+  const int c0 = S.c0;
+  if (bpos == 0) ordern_byte(S);
+  add(o, (stretch(T, sm32_p(T, S.sm0, y, c0)) + 1) >> 1);
+  add(o, (stretch(T, sm32_p(T, S.sm1, y, c0 | (buf(S, 1) << 8))) + 1) >> 1);
+  int order = cm2_mix(S.cm, o, y, bpos);
+  rcm_mix(S.rcm7, o, c0, bpos);
+  rcm_mix(S.rcm9, o, c0, bpos);
+  rcm_mix(S.rcm10, o, c0, bpos);
+  match_bit(S, o);
+  const int ismatch = ilog(T, S.match.length);
+  smatch_core(S, o);
+  smatch_select(S);
+  if (bpos == 0) { sparse_byte(S, ismatch, order); }
+  cm_mix(S.sparse.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  if (bpos == 0) sparse1_byte(S, ismatch, order);
+  cm_mix(S.sparse1.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  for (int k = 0; k < 7; ++k) scm_mix(S.sparse1.scm[k], o, y);
+  if (bpos == 0) distance_byte(S);
+  cm_mix(S.distance.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  pic_bit(S, o);
+  record_core(S, o, S.rnd);
+  record_select(S);
+  record1_bit(S, o, S.rnd);
+  if (bpos == 0) word_byte(S);
+  cm_mix(S.word.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  if (bpos == 0) nest_byte(S);
+  cm_mix(S.nest.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  if (bpos == 0) indirect_byte(S);
+  cm_mix(S.indirect.cm, o, S.rnd, y, c0, bpos, buf(S, 1));
+  dmc_bit(S, o);
+  xml_bit(S, o, S.rnd);
+  text_bit(S, o);
+  exe_bit(S, o);
+  linear_bit(S, o);
+  m.nx = o.n;
+  main_select(S, order);
   return mixer_predict(T, m, y, S.codes);
 }
 
-// PAQ8::Perceive(bit): paq8::y = bit; predictor_->update() (:8380-8383)
-P8_HD inline void bit(State& S, int y) {
+// bit bookkeeping of Predictor::update (:8251-8276)
+P8_HD inline void bit_begin(State& S, int y) {
   const Tables& T = *S.T;
   S.y = y;
   S.c0 += S.c0 + y;
@@ -824,7 +853,11 @@ P8_HD inline void bit(State& S, int y) {
   }
   S.bpos = (S.bpos + 1) & 7;
   S.grp0 = (S.bpos > 0) ? T.ascii_group_c0[(1 << S.bpos) - 2 + (S.c0 & ((1 << S.bpos) - 1))] : 0;
-  int pr0 = context_model(S);
+}
+// the SSE stage of Predictor::update (:8278-8358): APM chain on the mixer output pr0, exports behind the mixer's
+P8_HD inline void sse_stage(State& S, int pr0) {
+  const Tables& T = *S.T;
+  const int y = S.y;
   u16* codes = S.codes;
   int e = S.m.n2 + S.m.ncxt;
   codes[e++] = (u16)pr0;
@@ -861,6 +894,13 @@ P8_HD inline void bit(State& S, int y) {
   }
   S.pr = pr;
   S.last_prediction = pr;
+}
+
+// PAQ8::Perceive(bit): paq8::y = bit; predictor_->update() (:8380-8383) — the whole bit on one lane (CPU pinning)
+P8_HD inline void bit(State& S, int y) {
+  bit_begin(S, y);
+  const int pr0 = context_model(S);
+  sse_stage(S, pr0);
 }
 
 }  // namespace p8
