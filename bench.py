@@ -2,22 +2,23 @@
 """bench.py — throughput of the Predict()/Perceive() hot path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--step-bytes B]
-    python bench.py --impl reference ...           # the reference's own CPU implementation
+    python bench.py --impl reference ...           # the reference's own CPU implementation on the box's host cores
 
-A "step" is one pass of the hot path over one batch of synthetic input: every stream (one
-stream = one reference Predictor = one file) advances by --step-bytes bytes (8x as many coded
-bits). Workload = BASELINE.json configs[1] ("synthetic ... English-like text (enwik8 shape) on
-1xB200, full mixer + LSTM"): synthetic enwik-shaped text from tools/gen_synth.py; the model
-groups that are not device resident yet (PAQ8, FXCM: SURVEY §8 a13-a14) enter as synthetic
-replay streams of the same shape (2022 12-bit codes per bit). The PPMD byte model runs on the device
-(--ppmd resident, the default); --ppmd replay feeds a synthetic 256-float distribution per byte instead.
+Workload = BASELINE.json configs[1]: synthetic enwik8-shaped ASCII text (tools/gen_synth.py, seed 0xE9E80001),
+coded by the COMPLETE predictor: every model group (54 small models, PPMD, LSTM, FXCM, PAQ8, the 47 gated mixers, SSE)
+is device resident; the only input is the byte stream, the only output the probability of every bit. A "step" advances
+every stream by --step-bytes bytes (8x as many coded bits). One stream = one reference Predictor = one file.
 
-`value`  : input MB/s with every input already resident in HBM when the timed region starts.
-`e2e`    : the same metric through the C-ABI call with HOST (pinned) buffers, copies included.
-`roofline`: the mix kernel (dominant): algorithmic bytes (450 000 B per coded bit)
-            per launch / its CUDA-event duration on its own stream, against MEASURED_PEAKS.json.
-Multi-GPU (torchrun): streams are independent files, sharded across ranks with no data-path
-collective (weak scaling); time = max over ranks.
+`value`     input MB/s, streams' bytes already in HBM when the timed region starts. Default --streams 1: the single-file
+            figure every BASELINE config is about (latency bound: one bit depends on the previous one).
+`aggregate` the same with as many independent files per GPU as fit HBM (labelled; not the headline).
+`e2e`       `value`'s workload through cmixb200_code_batch with pinned HOST buffers: H2D of the step's bytes and D2H of
+            its probabilities inside the timed region.
+`roofline`  the gated-mixer kernel: 450 000 algorithmic B per coded bit / its CUDA-event duration on its own
+            stream, against MEASURED_PEAKS.json; `kernels` lists every bulk kernel's measured time per coded bit so that
+            the share of each (and the pole) is visible.
+`bpc`       cross entropy of the coded prefix from the device's probabilities, next to the reference's on the same bytes.
+Multi-GPU (torchrun): independent files per rank, no data-path collective (weak scaling); time = max over ranks.
 """
 import argparse
 import json
@@ -35,9 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-NCU_DRAM_BYTES_PER_BIT = 34786      # (63.16 MB read + 8.09 MB written) / 2048 bits of one launch, ncu --set full, profiles/r01_ncu_full_metrics.csv
-ALGO_BYTES_PER_BIT = 450_000          # 55 172 fp32 weights read + written, + input vectors
-N_EXT = 2022
+NCU_DRAM_BYTES_PER_BIT = 34786      # mix_kernel_v3: (63.16 MB read + 8.09 MB written) / 2048 bits, ncu --set full, profiles/r01_ncu_full_metrics.csv
+ALGO_BYTES_PER_BIT = 450_000        # 55 172 fp32 weights read + written, + input vectors
+KERNELS = ["mix_kernel_v3", "small_kernel", "lstm_kernel", "ppmd_kernel", "fxcm_kernel", "paq8_kernel"]
+SEED = 0xE9E80001
 
 
 def measured_hbm_peak():
@@ -52,9 +54,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.rows = []
-        self.stop_flag = False
-        self.index = index
+        self.rows, self.stop_flag, self.index = [], False, index
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -73,70 +73,44 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(r[2 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
+        reasons = [name for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"])
+                   if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
 
 
-def make_inputs(torch, dev, n_bytes, seed):
-    """Synthetic enwik-shaped text + replay streams of the right shape, generated on the device."""
+def bench_text(n_bytes, stream_id=0):
     from gen_synth import synth_text
-    text = np.frombuffer(synth_text(n_bytes, 0xE9E80001 + seed), dtype=np.uint8).copy()
-    vocab = np.zeros(256, dtype=np.uint8)
-    vocab[np.unique(text)] = 1
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + seed)
-    d_bytes = torch.from_numpy(text).to(dev)
-    bits = ((d_bytes[:, None] >> torch.arange(7, -1, -1, device=dev, dtype=torch.uint8)) & 1).reshape(-1).float()
-    skill = torch.rand(N_EXT, device=dev, generator=g) * 1.5
-    d_ext = torch.empty((n_bytes * 8, N_EXT), dtype=torch.int16, device=dev)
-    for lo in range(0, n_bytes * 8, 8192):           # chunked to bound temporaries
-        hi = min(lo + 8192, n_bytes * 8)
-        logit = torch.randn((hi - lo, N_EXT), device=dev, generator=g) * 1.2 + skill * (2 * bits[lo:hi, None] - 1)
-        d_ext[lo:hi] = torch.clamp(torch.round(4095.0 / (1.0 + torch.exp(-logit))), 0, 4095).to(torch.int16)
-    d_ext[:, 429:431] = -1                            # 0xFFFF: slots the reference never writes (0.5)
-    pp = torch.empty((n_bytes, 256), device=dev).exponential_(3.0, generator=g) + 1e-6
-    nxt = torch.roll(d_bytes.long(), -1)
-    pp[torch.arange(n_bytes, device=dev), nxt] += torch.rand(n_bytes, device=dev, generator=g) * 8
-    pp *= torch.from_numpy(vocab).to(dev)[None, :].float()
-    pp = (pp / pp.sum(dim=1, keepdim=True)).contiguous()
-    return text, vocab, d_bytes, d_ext, pp
+    return np.frombuffer(synth_text(n_bytes, SEED + stream_id), dtype=np.uint8).copy()
+
+
+def reference_run(binary, n_bytes, step_bytes):
+    """One process of the reference (oracle/ref_driver.cpp `time` mode, pinned to core 0) over the first n_bytes of the bench text."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "in.txt")
+        open(src, "wb").write(bench_text(n_bytes).tobytes())
+        cmd = [binary, "time", "n", src, str(n_bytes), "-", str(step_bytes)]
+        if subprocess.run(["which", "taskset"], capture_output=True).returncode == 0:
+            cmd = ["taskset", "-c", "0"] + cmd
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+        return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
 
 
 def cpu_baseline(sample_bytes):
-    """The reference's own CPU implementation on the box's host cores (single thread: it has no other).
-    Uses oracle/_ref/oracle_dump ("reference") when it travelled, else the oracle port ("port")."""
-    from gen_synth import synth_text
-    import tempfile
-    ref = os.path.join(ROOT, "oracle", "_ref", "oracle_dump")
-    with tempfile.TemporaryDirectory() as tmp:
-        src = os.path.join(tmp, "in.txt")
-        open(src, "wb").write(synth_text(sample_bytes, 0xE9E80001))
-        if os.path.exists(ref):
-            out = subprocess.run([ref, "time", "n", src, str(sample_bytes + 16)], capture_output=True, text=True, timeout=1800)
-            line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-            r = json.loads(line)
-            path_s = r["code_s"] - r["big_models_s"]
-            return {"value": r["bytes"] / path_s / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference",
-                    "sample": "first %d bytes of the synthetic text, cmix -n equivalent, g++ -O2 strict-FP build; "
-                              "time of the rows this repo has on the device (predictor total %.2f s minus PAQ8+FXCM+PPMD %.2f s; PPMD, now "
-                              "resident here too, is <1 %% of that and stays subtracted, which only favours the CPU); "
-                              "whole predictor: %.6f MB/s; constructor %.1f s excluded"
-                              % (r["bytes"], r["code_s"], r["big_models_s"], r["bytes"] / r["code_s"] / 1e6, r["ctor_s"]),
-                    "full_predictor_value": r["bytes"] / r["code_s"] / 1e6}
-    # port fallback: replay synthetic streams through the CPU restatement
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from conftest import port_replay, synthetic_streams
-    from oracle_io import load_port
-    stream, vocab, codes, ppmd = synthetic_streams(sample_bytes, seed=1)
-    lib = load_port()
-    t0 = time.time()
-    port_replay(lib, vocab, stream, codes, ppmd)
-    dt = time.time() - t0
-    return {"value": sample_bytes / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
-            "sample": "%d bytes of synthetic replay streams through oracle/port (scalar C++)" % sample_bytes}
+    """The unmodified reference on one host core (it has no threads): the project-flag build (-Ofast, makefile:4; -march=x86-64-v3
+    so that the binary built in the CPU container runs here) is the timed baseline, the strict-FP build (the parity oracle) is
+    reported next to it. Whole predictor, constructor excluded, `cmix -n` equivalent on the first sample_bytes of the bench text."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    fast, strict = os.path.join(ref, "oracle_dump_fast"), os.path.join(ref, "oracle_dump")
+    if not os.path.exists(strict):
+        return {"value": None, "unit": "MB/s", "cores": 1, "kind": "unavailable", "sample": "oracle/_ref not built (make -C oracle ref)"}
+    r_strict = reference_run(strict, sample_bytes, 0)
+    r_fast = reference_run(fast, sample_bytes, 0) if os.path.exists(fast) else None
+    r = r_fast or r_strict
+    return {"value": r["bytes"] / r["code_s"] / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
+            "build": "-Ofast -march=x86-64-v3 (project flags)" if r_fast else "-O2 strict FP",
+            "sample": "first %d bytes of the bench text, whole predictor, one stream, taskset -c 0, constructor (%.1f s) excluded" % (r["bytes"], r["ctor_s"]),
+            "strict_value": r_strict["bytes"] / r_strict["code_s"] / 1e6, "bpc_reference": r_strict["bpc"], "bpc_reference_fast_build": r_fast["bpc"] if r_fast else None}
 
 
 def main():
@@ -145,47 +119,44 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "24")), help="independent files per GPU")
-    ap.add_argument("--step-bytes", type=int, default=2048)
-    ap.add_argument("--ppmd", default=os.environ.get("CMIXB200_BENCH_PPMD", "resident"), choices=["resident", "replay"],
-                    help="PPMD byte model: resident on the device (ppmd.cuh) or a synthetic replayed distribution")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "1")), help="independent files per GPU for `value`")
+    ap.add_argument("--aggregate-streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_AGG", "6")), help="files per GPU for the aggregate figure (0 = skip)")
+    ap.add_argument("--step-bytes", type=int, default=1024)
     ap.add_argument("--cpu-sample-bytes", type=int, default=4096)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "configs[1]: synthetic enwik8-shaped ASCII text, full mixer + LSTM + small models; "
-                          "PAQ8/FXCM outputs as synthetic replay streams; PPMD %s" % ("resident on the device" if args.ppmd == "resident" else "replayed"),
-              "streams_per_gpu": args.streams, "step_bytes_per_stream": args.step_bytes,
-              "parallelism": "independent streams sharded over %d rank(s), no data-path collective" % max(world, args.gpus),
-              "l2": "inputs larger than L2: every step streams %.0f MB of fresh replay codes per stream and walks ~6 GB of "
-                    "per-stream HBM tables" % (args.step_bytes * 8 * N_EXT * 2 / 1e6)}
+    S, B, K, W = args.streams, args.step_bytes, args.steps, args.warmup
+    config = {"workload": "configs[1]: synthetic enwik8-shaped ASCII text (seed 0xE9E80001), `cmix -n` equivalent; complete predictor, every model "
+                          "group device resident (small models, PPMD, LSTM, FXCM, PAQ8, 47 mixers, SSE); no replayed inputs",
+              "streams_per_gpu": S, "step_bytes_per_stream": B,
+              "parallelism": "independent files sharded over %d rank(s), no data-path collective" % max(world, args.gpus),
+              "l2": "inputs larger than L2: every coded byte walks ~22 GB of per-stream HBM tables (hashed buckets of ~330 contexts, 40 mixer weight sets)"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # each "step" is a bounded sample; K+W steps of the same size, the first W discarded
-        sample = max(256, args.cpu_sample_bytes // 4)
-        vals = []
-        cb = None
-        for i in range(args.warmup + args.steps):
-            cb = cpu_baseline(sample)
-            if i >= args.warmup:
-                vals.append(cb["value"])
-            if i == 0 and args.warmup + args.steps > 2:
-                pass
-        v = float(np.mean(vals))
-        cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "input_MB_per_s", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample / v / 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": cb,
+        ref = os.path.join(ROOT, "oracle", "_ref")
+        binary = os.path.join(ref, "oracle_dump_fast") if os.path.exists(os.path.join(ref, "oracle_dump_fast")) else os.path.join(ref, "oracle_dump")
+        sample = max(256, min(B, 1024))                 # bounded sample per step: the reference needs ~2-5 ms per byte
+        r = reference_run(binary, sample * (W + K), sample)
+        steps = r["step_s"][W:W + K]
+        v = sample * len(steps) / sum(steps) / 1e6
+        cb = {"value": v, "unit": "MB/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
+              "build": "-Ofast -march=x86-64-v3 (project flags)" if binary.endswith("_fast") else "-O2 strict FP",
+              "sample": "%d steps of %d bytes of the bench text after %d warm-up steps, one process (constructor %.1f s excluded), one stream, taskset -c 0"
+                        % (len(steps), sample, W, r["ctor_s"])}
+        config["streams_per_gpu"] = 1
+        print(json.dumps({"impl": "reference", "metric": "input_MB_per_s", "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": sum(steps) / len(steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config, "cpu_baseline": cb, "bpc": r["bpc"],
                           "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
     import torch
     import cmix_b200
-    from cmix_b200.capi import code_batch_device
+    from cmix_b200.capi import code_batch, code_batch_device
     from cmix_b200.sharding import stream_block, reduce_timing
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
@@ -196,101 +167,92 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    S, B, K, W = args.streams, args.step_bytes, args.steps, args.warmup
-    total_steps = K + W
-    # ---- inputs resident in HBM before the timed region ----
-    streams = []
+    n_e2e = 10
+    total_steps = W + K + 1 + n_e2e + 3
+    S_total = max(S, args.aggregate_streams)
     free0 = torch.cuda.mem_get_info(dev)[0]
-    for s in stream_block(S * world, world, rank):      # global stream ids owned by this rank (weak scaling: S per GPU)
-        if len(streams) >= S:
+    streams = []
+    for s in stream_block(S_total * world, world, rank):
+        if len(streams) >= S_total:
             break
-        text, vocab, d_bytes, d_ext, d_ppmd = make_inputs(torch, dev, B * total_steps, seed=s)
+        text = bench_text(B * total_steps, stream_id=s)
+        vocab = np.zeros(256, dtype=np.uint8)
+        vocab[np.unique(text)] = 1
         P = cmix_b200.Predictor(vocab, device=local_rank)
-        d_out = torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)
-        streams.append(dict(P=P, text=text, d_bytes=d_bytes, d_ext=d_ext, d_ppmd=d_ppmd, d_out=d_out))
-        if len(streams) == 1:
-            # every stream owns ~7 GB of model tables: run as many streams as fit (the same number on every rank)
-            # instead of driving the box out of memory
-            per_stream = free0 - torch.cuda.mem_get_info(dev)[0] + 2 * 1024 * (8 * N_EXT * 2 + 256 * 4) + (64 << 20)
-            s_fit = max(1, int(0.94 * free0 // per_stream))
+        streams.append(dict(P=P, text=text, pos=0, d_bytes=torch.from_numpy(text).to(dev), d_out=torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)))
+        if len(streams) == 1:   # every stream owns ~22 GB of model tables: run as many as fit (the same number on every rank)
+            per_stream = free0 - torch.cuda.mem_get_info(dev)[0] + (256 << 20)
+            fit = max(1, int(0.94 * free0 // per_stream))
             if dist:
-                t_fit = torch.tensor([s_fit], device=dev, dtype=torch.int64)
+                t_fit = torch.tensor([fit], device=dev, dtype=torch.int64)
                 dist.all_reduce(t_fit, op=dist.ReduceOp.MIN)
-                s_fit = int(t_fit.item())
-            if s_fit < S:
-                config["streams_requested"] = S
-                S = s_fit
-                config["streams_per_gpu"] = S
+                fit = int(t_fit.item())
+            S_total = min(S_total, fit)
+            S = min(S, fit)
             config["hbm_per_stream_gb"] = round(per_stream / 1e9, 2)
+    config["streams_per_gpu"] = S
     torch.cuda.synchronize()
 
-    def run_step(i):
-        lo, hi = i * B, (i + 1) * B
-        code_batch_device([st["P"] for st in streams], [st["d_bytes"][lo:hi] for st in streams], B,
-                          [st["d_ext"][lo * 8:hi * 8] for st in streams],
-                          [st["d_ppmd"][lo:hi] for st in streams] if args.ppmd == "replay" else None,
-                          [st["d_out"][lo * 8:hi * 8] for st in streams])
+    def run(group, n_steps, timed_kernels=False):
+        """n_steps further steps of every stream in `group` (each continues at its own cursor);
+        returns (seconds max over ranks, bytes over all ranks, launches, kernel ms dict)."""
+        preds = [st["P"] for st in group]
+        if timed_kernels:
+            for p in preds:
+                p.time_mix_kernel(True)
+        launches0 = sum(p.kernel_launches for p in preds)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            code_batch_device(preds, [st["d_bytes"][st["pos"]:st["pos"] + B] for st in group], B, None, None,
+                              [st["d_out"][st["pos"] * 8:(st["pos"] + B) * 8] for st in group])
+            for st in group:
+                st["pos"] += B
+        ev1.record()
+        torch.cuda.synchronize()
+        dt = max(time.perf_counter() - t0, ev0.elapsed_time(ev1) / 1e3)
+        nbytes = len(group) * B * n_steps
+        if dist:
+            dt, nbytes = reduce_timing(dist, dev, dt, nbytes)
+            dist.barrier()
+        kms = {}
+        if timed_kernels:
+            for w, name in enumerate(KERNELS):
+                ms = n = 0
+                for p in preds:
+                    a, b = p.kernel_ms(w)
+                    ms += a
+                    n += b
+                kms[name] = (ms, n)
+            for p in preds:
+                p.time_mix_kernel(False)
+        return dt, nbytes, sum(p.kernel_launches for p in preds) - launches0, kms
 
-    for i in range(W):
-        run_step(i)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    for st in streams:
-        st["P"].time_mix_kernel(True)
-    launches0 = sum(st["P"].kernel_launches for st in streams)
+    head = streams[:S]
+    run(head, W)                                          # warm-up (untimed)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        run_step(i)                                   # synchronises its three library streams before returning
-    ev1.record()
-    torch.cuda.synchronize()
-    dt = max(time.perf_counter() - t0, ev0.elapsed_time(ev1) / 1e3)
+    dt, total_bytes, launches, kms = run(head, K, timed_kernels=True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    bytes_per_rank = S * B * K
-    total_bytes = bytes_per_rank * world
-    if dist:
-        dt, total_bytes = reduce_timing(dist, dev, dt, bytes_per_rank)
-        dist.barrier()
-    launches = sum(st["P"].kernel_launches for st in streams) - launches0
-    mix_ms, mix_n = 0.0, 0                              # summed over the launch-group leaders (others report 0)
-    for st in streams:
-        ms_, n_ = st["P"].mix_kernel_ms()
-        mix_ms += ms_
-        mix_n += n_
     value = total_bytes / dt / 1e6
 
-    # ---- end to end through the C-ABI with HOST (pinned) buffers: every stream of this rank, one more step ----
-    # The same predictors continue from where the device-resident run stopped; the step's inputs start in
-    # pinned host memory and its probabilities end there (cmixb200_code_batch stages them inside the call).
-    from cmix_b200.capi import code_batch
-    n_e2e = min(2, max(1, K + W - 1))                  # timed steps, after one untimed step that sizes the staging buffers
-    lo = (W + K - n_e2e - 1) * B
-    nb = (n_e2e + 1) * B
-    h_bytes = [torch.from_numpy(st["text"][lo:lo + nb].copy()).pin_memory() for st in streams]
-    h_ext = [st["d_ext"][lo * 8:(lo + nb) * 8].cpu().pin_memory() for st in streams]
-    h_ppmd = [st["d_ppmd"][lo:lo + nb].cpu().pin_memory() for st in streams]
-    h_out = [torch.empty(nb * 8, dtype=torch.float32).pin_memory() for _ in streams]
-    preds = [st["P"] for st in streams]
-
-    def e2e_step(j):
-        code_batch(preds, [t[j * B:] for t in h_bytes], B, [t[j * B * 8 * N_EXT:] for t in h_ext],
-                   [t[j * B * 256:] for t in h_ppmd] if args.ppmd == "replay" else None, [t[j * B * 8:] for t in h_out])
-
-    h_ext = [t.view(-1) for t in h_ext]
-    h_ppmd = [t.view(-1) for t in h_ppmd]
-    e2e_step(0)
+    # ---- end to end through the C-ABI with pinned HOST buffers: the same streams continue ----
+    preds = [st["P"] for st in head]
+    lo = (W + K) * B
+    h_bytes = [torch.from_numpy(st["text"][lo:lo + (n_e2e + 1) * B].copy()).pin_memory() for st in head]
+    h_out = [torch.empty((n_e2e + 1) * B * 8, dtype=torch.float32).pin_memory() for _ in head]
+    code_batch(preds, h_bytes, B, None, None, h_out)         # one untimed step sizes the staging buffers
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
     for j in range(1, n_e2e + 1):
-        e2e_step(j)
+        code_batch(preds, [t[j * B:] for t in h_bytes], B, None, None, [t[j * B * 8:] for t in h_out])
     torch.cuda.synchronize()
     dt_e2e = time.perf_counter() - t0
     if dist:
@@ -298,60 +260,73 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt_e2e = float(tt.item())
     e2e_value = S * n_e2e * B * world / dt_e2e / 1e6
-    h2d = S * (B + B * 8 * N_EXT * 2 + (B * 256 * 4 if args.ppmd == "replay" else 0) + B * 8 * 4)   # per rank: bytes + codes (+ PPMD) + decay table
-    d2h = S * B * 8 * 4
     if not all(bool(torch.isfinite(o).all()) and float(o.min()) >= 0.0 and float(o.max()) <= 1.0 for o in h_out):
         raise SystemExit("bench.py: end-to-end probabilities out of range")
 
-    # ---- the decoder's order: Predict()/Perceive(bit) one bit at a time on one stream (not part of `value`) ----
+    # ---- aggregate: as many independent files per GPU as fit HBM (labelled, not the headline) ----
+    aggregate = None
+    for st in head:
+        st["pos"] += (n_e2e + 1) * B                         # the end-to-end steps consumed these bytes
+    if S_total > S:
+        n_agg = 3
+        run(streams[S:], 1)                                  # the extra streams' first step is their warm-up
+        dt_a, bytes_a, _, _ = run(streams, n_agg)
+        aggregate = {"value": bytes_a / dt_a / 1e6, "unit": "MB/s", "streams_per_gpu": len(streams), "steps": n_agg,
+                     "note": "independent files advanced together in one launch set; each is an untouched single-stream predictor (the reference runs one per process)"}
+
+    # ---- the decoder's order on one stream (not part of `value`) ----
     lock = None
     if rank == 0:
-        P0 = streams[0]["P"]
-        n_lock = 128
-        bits = np.unpackbits(streams[0]["text"][:n_lock // 8])
+        P0 = head[0]["P"]
+        bits = np.unpackbits(head[0]["text"][:16])
         for b in bits[:16]:
             P0.Predict(); P0.Perceive(int(b))
         t0 = time.perf_counter()
         for b in bits[16:]:
             P0.Predict(); P0.Perceive(int(b))
-        P0.Predict()                                     # drains the last queued Perceive()
-        lock = {"us_per_bit": (time.perf_counter() - t0) / (n_lock - 16) * 1e6, "bits": n_lock - 16,
-                "note": "cmixb200_predict/perceive through ctypes, replay inputs at 0.5, host clock"}
+        P0.Predict()
+        lock = {"us_per_bit": (time.perf_counter() - t0) / (bits.size - 16) * 1e6, "bits": int(bits.size - 16), "note": "cmixb200_predict/perceive through ctypes, every model resident, host clock"}
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
-        # Launch groups run the same kernel concurrently (engine.cu RunPipelined), so the GPU-level figure is the
-        # per-launch bandwidth times the MEASURED mean number of launches in flight = sum of launch durations / wall
-        # time of the timed region (never more than the number of groups).
-        group = int(os.environ.get("CMIXB200_GROUP", "8")) or S
-        n_groups = (S + group - 1) // group
-        bits_per_launch = (S * B * K * 8) / max(mix_n, 1)
-        per_launch = ALGO_BYTES_PER_BIT * bits_per_launch / (mix_ms / max(mix_n, 1) / 1e3) / 1e9 if mix_ms > 0 else None
-        in_flight = min(float(n_groups), mix_ms / (dt * 1e3)) if mix_ms > 0 else None
-        achieved = per_launch * in_flight if per_launch else None
+        n_bits = S * B * K * 8
+        mix_ms, mix_n = kms.get("mix_kernel_v3", (0.0, 0))
+        bits_per_launch = n_bits / max(mix_n, 1)
+        achieved = ALGO_BYTES_PER_BIT * bits_per_launch / (mix_ms / max(mix_n, 1) / 1e3) / 1e9 if mix_ms > 0 else None
+        per_bit = {k: (v[0] * 1e3 / n_bits if n_bits else None) for k, v in kms.items()}      # us per coded bit (kernels overlap on their own streams)
+        pole = max(per_bit, key=lambda k: per_bit[k] or 0) if per_bit else None
+        p_dev = head[0]["d_out"][W * B * 8:(W + K) * B * 8].cpu().numpy().astype(np.float64)
+        bits_coded = np.unpackbits(head[0]["text"][W * B:(W + K) * B])
         out = {
-            "metric": "input_MB_per_s", "value": value, "unit": "MB/s", "n_gpus": world if world > 1 else args.gpus,
-            "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "metric": "input_MB_per_s", "value": value, "unit": "MB/s", "n_gpus": world if world > 1 else args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "all streams through cmixb200_code_batch with pinned host buffers; H2D of the step's inputs and D2H of its "
-                            "probabilities inside the timed region (bytes are per rank per step)"},
+            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": S * B, "d2h_bytes_per_step": S * B * 8 * 4, "steps": n_e2e,
+                    "note": "cmixb200_code_batch with pinned host buffers: the step's bytes go up and its probabilities come back inside the timed region (bytes per rank per step)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None,
+            "roofline": {"bound": "hbm", "kernel": "mix_kernel_v3", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": NCU_DRAM_BYTES_PER_BIT * bits_per_launch, "traffic_unit": "B per launch",
-                         "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 2048 bits",
-                         "kernel": "mix_kernel_v3", "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
-                         "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
-                         "launch_groups": n_groups, "mean_launches_in_flight": in_flight, "achieved_per_launch": per_launch,
-                         "note": "serial-dependency bound: each dot product is one fp32 FADD chain (bit-exact parity)"},
+                         "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 2048 bits (rows stay in shared memory)",
+                         "frac_dram": (NCU_DRAM_BYTES_PER_BIT / ALGO_BYTES_PER_BIT * achieved / peak) if achieved else None,
+                         "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind, "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
+                         "note": "latency bound, not bandwidth bound: every dot product is one serial fp32 FADD chain (bit-exact parity); frac_dram is the fraction of the HBM peak the kernel's measured DRAM traffic amounts to"},
+            "kernels": {"us_per_coded_bit": per_bit, "pole": pole, "note": "CUDA events on each kernel's own stream; the kernels of a sub-chunk overlap, the stream advances at the pole's pace"},
+            "single_stream": {"MB_per_s": value / max(S * world, 1), "hours_per_100MB": 100.0 / max(value / max(S * world, 1), 1e-12) / 3600.0},
+            "aggregate": aggregate,
             "bits_per_s": total_bytes * 8 / dt,
+            "bpc": float(-np.log2(np.where(bits_coded == 1, p_dev, 1 - p_dev).clip(1.0 / 65536, 1)).sum() / max(bits_coded.size // 8, 1)),
+            "bpc_note": "timed region of stream 0 (bytes %d..%d of the bench text); cpu_baseline.bpc_reference is the reference on its first cpu-sample bytes" % (W * B, (W + K) * B),
             "lockstep": lock,
         }
-        if (world == 1):
+        if world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.cpu_sample_bytes)
+                n = min(args.cpu_sample_bytes, (W + K) * B)
+                # the device's cross entropy on the same prefix the CPU sample covers
+                p0 = head[0]["d_out"][:n * 8].cpu().numpy().astype(np.float64)
+                b0 = np.unpackbits(head[0]["text"][:n])
+                out["bpc_on_cpu_sample"] = float(-np.log2(np.where(b0 == 1, p0, 1 - p0).clip(1.0 / 65536, 1)).sum() / n)
+                out["bpc_sample_bytes"] = n
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 1, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(out))

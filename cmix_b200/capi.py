@@ -67,6 +67,8 @@ def load_library():
     lib.cmixb200_time_mix_kernel.restype = None
     lib.cmixb200_mix_kernel_ms.argtypes = [vp, c.POINTER(c.c_ulonglong)]
     lib.cmixb200_mix_kernel_ms.restype = c.c_double
+    lib.cmixb200_kernel_ms.argtypes = [vp, c.c_int, c.POINTER(c.c_ulonglong)]
+    lib.cmixb200_kernel_ms.restype = c.c_double
     lib.cmixb200_mix_stream.argtypes = [vp]
     lib.cmixb200_mix_stream.restype = vp
     lib.cmixb200_debug_fetch.argtypes = [vp, c.c_int, vp, c.c_size_t]
@@ -184,6 +186,12 @@ class Predictor:
     def mix_kernel_ms(self):
         n = ctypes.c_ulonglong(0)
         ms = self._lib.cmixb200_mix_kernel_ms(self._h, ctypes.byref(n))
+        return float(ms), int(n.value)
+
+    def kernel_ms(self, which):
+        """(total ms, launches) of one bulk kernel since time_mix_kernel(True): 0 mix, 1 small, 2 lstm, 3 ppmd, 4 fxcm, 5 paq8."""
+        n = ctypes.c_ulonglong(0)
+        ms = self._lib.cmixb200_kernel_ms(self._h, int(which), ctypes.byref(n))
         return float(ms), int(n.value)
 
     @property

@@ -301,6 +301,8 @@ struct cmixb200_predictor {
   unsigned long long* d_prof = nullptr;
   bool time_mix = false; double mix_ms = 0.0; unsigned long long mix_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_ev;
+  struct KEv { int which; cudaEvent_t a, b; };
+  std::vector<KEv> pending_kev; double kernel_ms[6] = {0, 0, 0, 0, 0, 0}; unsigned long long kernel_n[6] = {0, 0, 0, 0, 0, 0};
   u8 vocab[256];
   int V = 0;
   Tables T;                            // this device's shared read-only tables (copied at create: no global is read at launch)
@@ -613,6 +615,12 @@ void HarvestMixTimes(cmixb200_predictor* P) {
     cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
   }
   P->pending_ev.clear();
+  for (auto& ev : P->pending_kev) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { P->kernel_ms[ev.which] += ms; P->kernel_n[ev.which]++; }
+    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+  }
+  P->pending_kev.clear();
 }
 
 // Launch the bulk kernels of one sub-chunk for a batch of streams whose ChunkArgs are already on the device:
@@ -620,32 +628,45 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false,
                 bool with_ppmd = false, bool with_fx = false, bool with_p8 = false) {
   const Tables T = lead->T;
+  // optional CUDA-event timing of every kernel on the stream it is launched on (bench.py)
+  auto tick = [&](cudaStream_t st) -> cudaEvent_t { cudaEvent_t e = nullptr; if (lead->time_mix) { cudaEventCreate(&e); cudaEventRecord(e, st); } return e; };
+  auto tock = [&](int which, cudaEvent_t a, cudaStream_t st) { if (a) { cudaEvent_t b = nullptr; cudaEventCreate(&b); cudaEventRecord(b, st); lead->pending_kev.push_back({which, a, b}); } };
   for (int i = 0; i < 8; ++i) if (!lead->ev[i]) CK(cudaEventCreateWithFlags(&lead->ev[i], cudaEventDisableTiming));
   if (with_ppmd && !pretrain) {
     // the PPMD producer runs ahead on its own stream; both consumers of its distributions wait for this sub-chunk's
+    { cudaEvent_t t = tick(lead->s_ppmd);
     ppmd_kernel<<<(n_streams + PPMD_WARPS - 1) / PPMD_WARPS, PPMD_WARPS * 32, PPMD_WARPS * sizeof(PpmdWarpShared), lead->s_ppmd>>>(d_args, n_streams);
+    tock(3, t, lead->s_ppmd); }
     lead->launches++;
     CK(cudaEventRecord(lead->ev[0], lead->s_ppmd));
     CK(cudaStreamWaitEvent(lead->s_small, lead->ev[0], 0));
     CK(cudaStreamWaitEvent(lead->s_lstm, lead->ev[0], 0));
   }
+  { cudaEvent_t t = tick(lead->s_small);
   small_kernel<<<n_streams, 64, sizeof(SmallState), lead->s_small>>>(d_args, T);
+  tock(1, t, lead->s_small); }
   lead->launches++;
   if (with_p8) {   // PAQ8 depends on the coded bytes only: it starts at once on its own stream
+    { cudaEvent_t t = tick(lead->s_p8);
     paq8_kernel<<<n_streams, P8_THREADS, sizeof(P8Shared), lead->s_p8>>>(d_args);
+    tock(5, t, lead->s_p8); }
     lead->launches++;
   }
   if (pretrain) {
     if (with_fx) { fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args); lead->launches++; }
   } else {
+    { cudaEvent_t t = tick(lead->s_lstm);
     lstm_kernel<<<LSTM_CTAS * n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
+    tock(2, t, lead->s_lstm); }
     lead->launches++;
     CK(cudaEventRecord(lead->ev[1], lead->s_small));
     CK(cudaEventRecord(lead->ev[2], lead->s_lstm));
     if (with_fx) {
       // FXCM consumes the LSTM's bit read-outs of this sub-chunk (lstmpr / lstmex) and produces 431 codes per bit
       CK(cudaStreamWaitEvent(lead->s_fx, lead->ev[2], 0));
+      { cudaEvent_t t = tick(lead->s_fx);
       fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args);
+      tock(4, t, lead->s_fx); }
       lead->launches++;
       CK(cudaEventRecord(lead->ev[3], lead->s_fx));
       CK(cudaStreamWaitEvent(lead->s_mix, lead->ev[3], 0));
@@ -902,7 +923,7 @@ int cmixb200_feed_external_bit(cmixb200_predictor* P, const uint16_t* codes) {
   CK(cudaStreamSynchronize(P->s_mix));           // the resident models of the previous Perceive() write d_ext_bit on s_mix
   // slots of resident models are produced on the device; only the replayed ones are taken from the caller
   // slots [first, last) are replayed
-  const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? fx::N_OUT : N_EXT;
+  const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? (size_t)fx::N_OUT : (size_t)N_EXT;
   if (last > first) CK(cudaMemcpy(P->d_ext_bit + first, codes + first, (last - first) * 2, cudaMemcpyHostToDevice));
   P->ext_bit_valid = true;
   return CMIXB200_OK;
@@ -933,7 +954,7 @@ float cmixb200_predict(cmixb200_predictor* P) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
   if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
   if (P->ext_bit_valid) {   // replayed slots fall back to "0.5" until they are fed again
-    const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? fx::N_OUT : N_EXT;
+    const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? (size_t)fx::N_OUT : (size_t)N_EXT;
     if (last > first) cudaMemsetAsync(P->d_ext_bit + first, 0xFF, (last - first) * 2, P->s_mix);
   }
   P->ext_bit_valid = false;
@@ -1112,7 +1133,13 @@ int cmixb200_coder_finish(cmixb200_predictor* P, uint8_t* out, size_t cap, size_
 }
 
 unsigned long long cmixb200_kernel_launches(const cmixb200_predictor* P) { return P->launches; }
-void cmixb200_time_mix_kernel(cmixb200_predictor* P, int enable) { P->time_mix = enable != 0; if (enable) { P->mix_ms = 0; P->mix_launches = 0; } }
+void cmixb200_time_mix_kernel(cmixb200_predictor* P, int enable) { P->time_mix = enable != 0; if (enable) { P->mix_ms = 0; P->mix_launches = 0; for (int i = 0; i < 6; ++i) { P->kernel_ms[i] = 0; P->kernel_n[i] = 0; } } }
+double cmixb200_kernel_ms(const cmixb200_predictor* P, int which, unsigned long long* n_launches) {
+  if (which == 0) { if (n_launches) *n_launches = P->mix_launches; return P->mix_ms; }
+  if (which < 0 || which > 5) return 0.0;
+  if (n_launches) *n_launches = P->kernel_n[which];
+  return P->kernel_ms[which];
+}
 double cmixb200_mix_kernel_ms(const cmixb200_predictor* P, unsigned long long* n_launches) { if (n_launches) *n_launches = P->mix_launches; return P->mix_ms; }
 void* cmixb200_mix_stream(cmixb200_predictor* P) { return (void*)P->s_mix; }
 

@@ -11,7 +11,9 @@
 //
 // Usage:
 //   oracle_dump dump <n|c|t> <input> <out_prefix> <level> [max_bytes] [dictionary]
-//   oracle_dump time <n|c|t> <input> <max_bytes> [dictionary]
+//   oracle_dump time <n|c|t> <input> <max_bytes> [dictionary|-] [step_bytes]
+//       step_bytes > 0: also report the wall time of every step_bytes-sized step (one constructor for a whole
+//       warm-up + timed series) and the cross entropy (bits per byte) of the coded prefix
 //
 //   n = no preprocessing (runner.cpp:187 -> preprocessor::NoPreprocess)
 //   c = preprocessing     (runner.cpp:184 -> preprocessor::Encode)
@@ -113,7 +115,7 @@ int main(int argc, char** argv) {
   std::string input_path = argv[3];
   std::string prefix;
   int level = 0;
-  unsigned long long max_bytes = ~0ULL;
+  unsigned long long max_bytes = ~0ULL, step_bytes = 0;
   const char* dict = NULL;
   if (cmd == "dump") {
     if (argc < 6) return 1;
@@ -123,7 +125,8 @@ int main(int argc, char** argv) {
     if (argc > 7) dict = argv[7];
   } else if (cmd == "time") {
     max_bytes = strtoull(argv[4], 0, 10);
-    if (argc > 5) dict = argv[5];
+    if (argc > 5 && strcmp(argv[5], "-") != 0) dict = argv[5];
+    if (argc > 6) step_bytes = strtoull(argv[6], 0, 10);
     prefix = "/tmp/oracle_time_" + std::to_string((long)getpid());
   } else {
     return 1;
@@ -232,13 +235,17 @@ int main(int argc, char** argv) {
   // Orchestration below mirrors predictor.cpp:361-469 statement for statement;
   // the arithmetic is all inside the reference's own objects.
   double t_big = 0;      // PAQ8 + FXCM + PPMD
-  double checksum = 0;
-  double t0 = now_s();
+  double checksum = 0, entropy_bits = 0;
+  std::vector<double> step_s;
+  double t0 = now_s(), t_step = t0;
   for (unsigned long long pos = 0; pos < n_bytes; ++pos) {
+    if (step_bytes && pos && pos % step_bytes == 0) { double t = now_s(); step_s.push_back(t - t_step); t_step = t; }
     unsigned char c = stream[pos];
     for (int j = 7; j >= 0; --j) {
       int bit = (c >> j) & 1;
-      checksum += p.Predict();
+      float pr = p.Predict();
+      checksum += pr;
+      { double q = bit ? pr : 1.0 - pr; if (q < 1.0 / 65536) q = 1.0 / 65536; entropy_bits -= log2(q); }
       // ---- Perceive (predictor.cpp:421-469) with timers ----
       for (unsigned int i = 0; i < p.models_.size(); ++i) {
         if (i == p.fxcm_index_) continue;
@@ -279,9 +286,12 @@ int main(int argc, char** argv) {
     }
   }
   double t1 = now_s();
+  if (step_bytes && n_bytes && n_bytes % step_bytes == 0) step_s.push_back(t1 - t_step);
   remove(temp_path.c_str());
   printf("{\"bytes\": %llu, \"ctor_s\": %.4f, \"pretrain_s\": %.4f, \"code_s\": %.6f, "
-         "\"big_models_s\": %.6f, \"checksum\": %.9f}\n",
-         n_bytes, t_ctor - t_start, t_pretrain - t_ctor, t1 - t0, t_big, checksum);
+         "\"big_models_s\": %.6f, \"checksum\": %.9f, \"bpc\": %.6f, \"step_bytes\": %llu, \"step_s\": [",
+         n_bytes, t_ctor - t_start, t_pretrain - t_ctor, t1 - t0, t_big, checksum, n_bytes ? entropy_bits / n_bytes : 0.0, step_bytes);
+  for (size_t i = 0; i < step_s.size(); ++i) printf("%s%.6f", i ? ", " : "", step_s[i]);
+  printf("]}\n");
   return 0;
 }
