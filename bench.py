@@ -83,12 +83,23 @@ def bench_text(n_bytes, stream_id=0):
     return np.frombuffer(synth_text(n_bytes, SEED + stream_id), dtype=np.uint8).copy()
 
 
-def reference_run(binary, n_bytes, step_bytes):
-    """One process of the reference (oracle/ref_driver.cpp `time` mode, pinned to core 0) over the first n_bytes of the bench text."""
+N_E2E = 10
+N_AGG = 3
+
+
+def file_bytes(B, W, K):
+    """Length of the synthetic file of one stream: every step of the run consumes fresh bytes of it. The vocabulary (the LSTM's
+    symbol set, runner.cpp:196-203) is taken over the whole file, in both arms."""
+    return B * (W + K + 1 + N_E2E + N_AGG)
+
+
+def reference_run(binary, n_file, n_bytes, step_bytes):
+    """One process of the reference (oracle/ref_driver.cpp `time` mode, pinned to core 0) coding the first n_bytes of the
+    n_file-byte bench text of stream 0."""
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
         src = os.path.join(tmp, "in.txt")
-        open(src, "wb").write(bench_text(n_bytes).tobytes())
+        open(src, "wb").write(bench_text(n_file).tobytes())
         cmd = [binary, "time", "n", src, str(n_bytes), "-", str(step_bytes)]
         if subprocess.run(["which", "taskset"], capture_output=True).returncode == 0:
             cmd = ["taskset", "-c", "0"] + cmd
@@ -96,7 +107,7 @@ def reference_run(binary, n_bytes, step_bytes):
         return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
 
 
-def cpu_baseline(sample_bytes):
+def cpu_baseline(n_file, sample_bytes):
     """The unmodified reference on one host core (it has no threads): the project-flag build (-Ofast, makefile:4; -march=x86-64-v3
     so that the binary built in the CPU container runs here) is the timed baseline, the strict-FP build (the parity oracle) is
     reported next to it. Whole predictor, constructor excluded, `cmix -n` equivalent on the first sample_bytes of the bench text."""
@@ -104,12 +115,12 @@ def cpu_baseline(sample_bytes):
     fast, strict = os.path.join(ref, "oracle_dump_fast"), os.path.join(ref, "oracle_dump")
     if not os.path.exists(strict):
         return {"value": None, "unit": "MB/s", "cores": 1, "kind": "unavailable", "sample": "oracle/_ref not built (make -C oracle ref)"}
-    r_strict = reference_run(strict, sample_bytes, 0)
-    r_fast = reference_run(fast, sample_bytes, 0) if os.path.exists(fast) else None
+    r_strict = reference_run(strict, n_file, sample_bytes, 0)
+    r_fast = reference_run(fast, n_file, sample_bytes, 0) if os.path.exists(fast) else None
     r = r_fast or r_strict
     return {"value": r["bytes"] / r["code_s"] / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
             "build": "-Ofast -march=x86-64-v3 (project flags)" if r_fast else "-O2 strict FP",
-            "sample": "first %d bytes of the bench text, whole predictor, one stream, taskset -c 0, constructor (%.1f s) excluded" % (r["bytes"], r["ctor_s"]),
+            "sample": "first %d bytes of the same file as stream 0 (same vocabulary), whole predictor, one stream, taskset -c 0, constructor (%.1f s) excluded" % (r["bytes"], r["ctor_s"]),
             "strict_value": r_strict["bytes"] / r_strict["code_s"] / 1e6, "bpc_reference": r_strict["bpc"], "bpc_reference_fast_build": r_fast["bpc"] if r_fast else None}
 
 
@@ -140,7 +151,7 @@ def main():
         ref = os.path.join(ROOT, "oracle", "_ref")
         binary = os.path.join(ref, "oracle_dump_fast") if os.path.exists(os.path.join(ref, "oracle_dump_fast")) else os.path.join(ref, "oracle_dump")
         sample = max(256, min(B, 1024))                 # bounded sample per step: the reference needs ~2-5 ms per byte
-        r = reference_run(binary, sample * (W + K), sample)
+        r = reference_run(binary, file_bytes(B, W, K), sample * (W + K), sample)
         steps = r["step_s"][W:W + K]
         v = sample * len(steps) / sum(steps) / 1e6
         cb = {"value": v, "unit": "MB/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
@@ -167,8 +178,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    n_e2e = 10
-    total_steps = W + K + 1 + n_e2e + 3
+    n_e2e = N_E2E
+    total_steps = file_bytes(B, W, K) // B
     S_total = max(S, args.aggregate_streams)
     free0 = torch.cuda.mem_get_info(dev)[0]
     streams = []
@@ -176,8 +187,10 @@ def main():
         if len(streams) >= S_total:
             break
         text = bench_text(B * total_steps, stream_id=s)
-        vocab = np.zeros(256, dtype=np.uint8)
-        vocab[np.unique(text)] = 1
+        vocab = np.ones(256, dtype=np.uint8)
+        if text.size >= 10000:                               # runner.cpp:14,197: short files keep the full symbol set
+            vocab[:] = 0
+            vocab[np.unique(text)] = 1
         P = cmix_b200.Predictor(vocab, device=local_rank)
         streams.append(dict(P=P, text=text, pos=0, d_bytes=torch.from_numpy(text).to(dev), d_out=torch.empty(B * total_steps * 8, dtype=torch.float32, device=dev)))
         if len(streams) == 1:   # every stream owns ~22 GB of model tables: run as many as fit (the same number on every rank)
@@ -268,7 +281,7 @@ def main():
     for st in head:
         st["pos"] += (n_e2e + 1) * B                         # the end-to-end steps consumed these bytes
     if S_total > S:
-        n_agg = 3
+        n_agg = N_AGG
         run(streams[S:], 1)                                  # the extra streams' first step is their warm-up
         dt_a, bytes_a, _, _ = run(streams, n_agg)
         aggregate = {"value": bytes_a / dt_a / 1e6, "unit": "MB/s", "streams_per_gpu": len(streams), "steps": n_agg,
@@ -320,7 +333,7 @@ def main():
         }
         if world == 1:
             try:
-                out["cpu_baseline"] = cpu_baseline(args.cpu_sample_bytes)
+                out["cpu_baseline"] = cpu_baseline(file_bytes(B, W, K), args.cpu_sample_bytes)
                 n = min(args.cpu_sample_bytes, (W + K) * B)
                 # the device's cross entropy on the same prefix the CPU sample covers
                 p0 = head[0]["d_out"][:n * 8].cpu().numpy().astype(np.float64)

@@ -13,9 +13,10 @@ import numpy as np
 N_EXT = 2022
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libcmixb200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+LIB_PATH = os.environ.get("CMIXB200_LIB") or os.path.join(CSRC, "libcmixb200.so")   # CMIXB200_LIB: a profiling build (tools/prof_build.py)
+NVCC_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = NVCC_COMPILE + ["-shared"]
 
 _lib = None
 
@@ -26,8 +27,16 @@ def build_library(force=False):
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "cmixb200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + [os.path.join(CSRC, "engine.cu"), "-o", LIB_PATH]
-    subprocess.run(cmd, check=True)
+    units = ["engine.cu", "fxcm_dev.cu", "paq8_dev.cu"]
+    objs, jobs = [], []
+    for u in units:                                   # the three device programs compile side by side
+        obj = os.path.join(CSRC, u[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or any(os.path.getmtime(obj) < os.path.getmtime(s) for s in srcs):
+            jobs.append(subprocess.Popen(["nvcc"] + NVCC_COMPILE + ["-c", os.path.join(CSRC, u), "-o", obj]))
+    if any(j.wait() != 0 for j in jobs):
+        raise RuntimeError("cmix_b200: nvcc failed")
+    subprocess.run(["nvcc"] + NVCC_LINK + objs + ["-o", LIB_PATH], check=True)
     return LIB_PATH
 
 

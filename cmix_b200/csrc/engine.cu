@@ -28,10 +28,11 @@
 #include "../../include/cmixb200.h"
 #include "exact_math.h"
 #include "coder.cuh"
-#include "fxcm.cuh"
+#include "fxcm_model.h"
 #include "fxcm_host.h"
-#include "paq8.cuh"
+#include "paq8_top.h"
 #include "paq8_host.h"
+#include "producers.h"
 #include "lstm.cuh"
 #include "mixer.cuh"
 #include "mixer_v3.cuh"
@@ -263,10 +264,8 @@ int BuildSharedTablesLocked(int device, SharedTables& g_tables) {
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
   CK(cudaFuncSetAttribute(ppmd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PPMD_WARPS * sizeof(PpmdWarpShared))));
   CK(cudaFuncSetAttribute(lstm_byte_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));
-  CK(cudaFuncSetAttribute(fxcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
-  CK(cudaFuncSetAttribute(fxcm_bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FxShared)));
-  CK(cudaFuncSetAttribute(paq8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P8Shared)));
-  CK(cudaFuncSetAttribute(paq8_bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P8Shared)));
+  CK(fxcm_configure());
+  CK(paq8_configure());
   g_tables.ready = true;
   return CMIXB200_OK;
 }
@@ -392,7 +391,12 @@ int BuildPaq8(cmixb200_predictor* P) {
   p8::Tables* T = new p8::Tables();
   p8::build_tables(*T);
   int r = P->Alloc(&P->d_p8_tables, 1, false);
-  if (r == CMIXB200_OK && cudaMemcpy(P->d_p8_tables, T, sizeof *T, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "PAQ8 table upload failed"; r = CMIXB200_ERR_CUDA; }
+  if (r == CMIXB200_OK) {
+    p8::Tables* up = new p8::Tables(*T);               // the device copy's ilog pointer addresses the device copy
+    up->ilog = reinterpret_cast<const u8*>(P->d_p8_tables) + offsetof(p8::Tables, ilog_store);
+    if (cudaMemcpy(P->d_p8_tables, up, sizeof *up, cudaMemcpyHostToDevice) != cudaSuccess) { g_last_error = "PAQ8 table upload failed"; r = CMIXB200_ERR_CUDA; }
+    delete up;
+  }
   p8::State* S = new p8::State();
   if (r == CMIXB200_OK) {
     DeviceBackend be{P};
@@ -648,12 +652,12 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
   lead->launches++;
   if (with_p8) {   // PAQ8 depends on the coded bytes only: it starts at once on its own stream
     { cudaEvent_t t = tick(lead->s_p8);
-    paq8_kernel<<<n_streams, P8_THREADS, sizeof(P8Shared), lead->s_p8>>>(d_args);
+    paq8_launch_chunk(d_args, n_streams, lead->s_p8);
     tock(5, t, lead->s_p8); }
     lead->launches++;
   }
   if (pretrain) {
-    if (with_fx) { fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args); lead->launches++; }
+    if (with_fx) { fxcm_launch_chunk(d_args, n_streams, lead->s_fx); lead->launches++; }
   } else {
     { cudaEvent_t t = tick(lead->s_lstm);
     lstm_kernel<<<LSTM_CTAS * n_streams, LSTM_THREADS, sizeof(LstmShared), lead->s_lstm>>>(d_args, T);
@@ -665,7 +669,7 @@ int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool
       // FXCM consumes the LSTM's bit read-outs of this sub-chunk (lstmpr / lstmex) and produces 431 codes per bit
       CK(cudaStreamWaitEvent(lead->s_fx, lead->ev[2], 0));
       { cudaEvent_t t = tick(lead->s_fx);
-      fxcm_kernel<<<n_streams, FX_THREADS, sizeof(FxShared), lead->s_fx>>>(d_args);
+      fxcm_launch_chunk(d_args, n_streams, lead->s_fx);
       tock(4, t, lead->s_fx); }
       lead->launches++;
       CK(cudaEventRecord(lead->ev[3], lead->s_fx));
@@ -981,8 +985,8 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
   if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
   // FXCM is perceived last and sees the LSTM's read-out of the next bit (predictor.cpp:462-466)
-  if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 0, P->d_ext_bit); P->launches++; }
-  if (P->d_p8) { paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), P->s_mix>>>(P->d_p8, bit, P->d_ext_bit); P->launches++; }
+  if (P->d_fx) { fxcm_launch_bit(P->d_st, P->d_fx, bit, 0, P->d_ext_bit, P->s_mix); P->launches++; }
+  if (P->d_p8) { paq8_launch_bit(P->d_p8, bit, P->d_ext_bit, P->s_mix); P->launches++; }
   CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
   P->launches += 2;
   CK(cudaGetLastError());
@@ -1000,8 +1004,8 @@ int cmixb200_pretrain(cmixb200_predictor* P, int bit) {
   small_predict_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, T);
   small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, nullptr, 1);
   P->launches += 2;
-  if (P->d_fx) { fxcm_bit_kernel<<<1, FX_THREADS, sizeof(FxShared), P->s_mix>>>(P->d_st, P->d_fx, bit, 1, P->d_ext_bit); P->launches++; }
-  if (P->d_p8) { paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), P->s_mix>>>(P->d_p8, bit, P->d_ext_bit); P->launches++; }
+  if (P->d_fx) { fxcm_launch_bit(P->d_st, P->d_fx, bit, 1, P->d_ext_bit, P->s_mix); P->launches++; }
+  if (P->d_p8) { paq8_launch_bit(P->d_p8, bit, P->d_ext_bit, P->s_mix); P->launches++; }
   CK(cudaGetLastError());
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   return CMIXB200_OK;

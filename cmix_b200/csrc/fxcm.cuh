@@ -13,18 +13,28 @@
 #pragma once
 #include "exact_math.h"
 #include "fxcm_model.h"
-#include "small_models.cuh"
+#include "bytemodel.cuh"
 #include "state.h"
 
 namespace cmixb200 {
 
 enum { FX_THREADS = 128 };
 
+#ifdef FX_PROF
+__device__ unsigned long long g_fx_prof[2][24];
+#define FX_T(k) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_fx_prof[sh.prof_row][k], (unsigned long long)(now_ - sh.prof_t)); sh.prof_t = now_; } } while (0)
+#else
+#define FX_T(k) do { } while (0)
+#endif
+
 struct FxShared {
   fx::State S;
   fx::TextState X;
   int part[4][10];
   int dots[10];
+#ifdef FX_PROF
+  long long prof_t; int prof_row;
+#endif
 };
 
 __device__ __forceinline__ int fx_unit_of(int tid) {
@@ -62,17 +72,25 @@ __device__ __forceinline__ void fx_store(FxShared& sh, fx::State* g, fx::TextSta
 // One bit: FXCM::Perceive(bit) (fxcmv1.cpp:4909-4912 -> update1 :4758). All FX_THREADS lanes call it.
 __device__ void fx_bit(FxShared& sh, int y, int lstmpr, int lstmex, int tid) {
   fx::State& S = sh.S;
+#ifdef FX_PROF
+  if (tid == 0) { sh.prof_t = clock64(); sh.prof_row = (S.bpos == 7) ? 0 : 1; }
+#endif
   if (tid == 0) fx::bit_head(S, y, lstmpr, lstmex);
   __syncthreads();
+  FX_T(0);
   fx::bit_train(S, tid, FX_THREADS);
   __syncthreads();
+  FX_T(1);
   if (tid == 0) fx::bit_prepare(S);
   __syncthreads();
+  FX_T(2);
   const int u = fx_unit_of(tid);
   if (u >= 0) fx::bit_unit(S, u);
   __syncthreads();
+  FX_T(3);
   if (tid == 0) fx::bit_select(S);
   __syncthreads();
+  FX_T(4);
   {
     int part[10];
     fx::bit_dot_partial(S, tid, FX_THREADS, part);
@@ -81,12 +99,14 @@ __device__ void fx_bit(FxShared& sh, int y, int lstmpr, int lstmex, int tid) {
     if ((tid & 31) == 0) for (int i = 0; i < 10; ++i) sh.part[tid >> 5][i] = part[i];
   }
   __syncthreads();
+  FX_T(5);
   if (tid == 0) {
     int dots[10];
     for (int i = 0; i < 10; ++i) dots[i] = sh.part[0][i] + sh.part[1][i] + sh.part[2][i] + sh.part[3][i];
     fx::bit_tail(S, dots);
   }
   __syncthreads();
+  FX_T(6);
 }
 
 // Bulk: CTA b serves stream b of the launch group. Writes ext[t][0..430] for every bit t of the sub-chunk (the codes

@@ -26,6 +26,7 @@ inline void unhex(u8* dst, int n, const char* hex) {
 
 inline void build_tables(Tables& T) {
   memset(&T, 0, sizeof T);
+  T.ilog = T.ilog_store;
   unhex(&T.state[0][0], 1024,
       "010200000305010004060001070a0200080c0101090d01010b0e00020f130300101702011118020112190201141b0102"
       "151c0102161d01021a1e00031f2104002023030120230301202303012023030122250202222502022225020222250202"
@@ -141,7 +142,7 @@ inline void build_tables(Tables& T) {
   }
   {   // Ilog (paq8.cpp:260-266)
     u32 x = 14155776;
-    for (int i = 2; i < 65536; ++i) { x += 774541002 / (i * 2 - 1); T.ilog[i] = (u8)(x >> 24); }
+    for (int i = 2; i < 65536; ++i) { x += 774541002 / (i * 2 - 1); T.ilog_store[i] = (u8)(x >> 24); }
   }
   for (int i = 0; i < 1024; ++i) T.dt[i] = 16384 / (i + i + 3);
 }

@@ -17,6 +17,7 @@
 #ifndef CMIXB200_PAQ8_MODEL_H
 #define CMIXB200_PAQ8_MODEL_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -45,17 +46,20 @@ P8_HD inline u32 umin(u32 a, u32 b) { return a < b ? a : b; }
 
 // ---------------------------------------------------------------- read-only tables (host-built, paq8_host.h)
 struct Tables {
+  const u8* ilog;        // -> ilog_store below (kept out of line so that everything before ilog_store can be staged in shared memory)
   u8 state[256][4];      // State_table (paq8.cpp:277-341)
   u16 squash[4096];      // index p + 2048 (:345-367)
   short stretch[4096];   // (:369-387)
-  u8 ilog[65536];        // (:253-266)
   int dt[1024];          // 16384 / (i + i + 3) (:8244)
   u8 ascii_group_c0[254], ascii_group[128];   // (:3039-3068)
   // x86 decoder tables (:6580-7040) as produced by the reference's own initialisers
   u8 exe_t1[256], exe_t2[256], exe_t3_38[256], exe_t3_3a[256], exe_tx[32];
   u8 exe_c1[256], exe_c2[256], exe_c3_38[256], exe_c3_3a[256], exe_cx[32];
   u8 exe_invalid64[19], exe_prefix64[8];
+  alignas(16) u8 ilog_store[65536];   // (:253-266)
 };
+enum { TABLES_HOT_BYTES = offsetof(Tables, ilog_store) };
+static_assert(TABLES_HOT_BYTES % 16 == 0, "the hot part of the tables is copied in 16-byte words");
 
 P8_HD inline int squash(const Tables& T, int p) { if (p > 2047) return 4095; if (p < -2047) return 0; return T.squash[p + 2048]; }
 P8_HD inline int stretch(const Tables& T, int p) { return T.stretch[p]; }
@@ -129,7 +133,7 @@ struct Dmc { DmcNode* t; Sm32 sm; u32 size, top, curr, threshold, threshold_fine
 struct Mixer {
   short* w;              // [N_WSETS][N_IN] dense (the reference allocates sets lazily; zero-use sets never differ from fresh ones)
   short* w2;             // final mixer: one set of 32
-  short tx[N_IN]; short tx2[32];
+  alignas(16) short tx[N_IN]; alignas(16) short tx2[32];
   int cxt[N_SETS], pr[N_SETS];
   int ncxt, base, nx, nx2, pr2, n2;
 };

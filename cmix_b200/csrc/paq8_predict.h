@@ -13,7 +13,7 @@
 namespace cmixb200 {
 namespace p8 {
 
-enum { ERR_UNSUPPORTED_BLOCK = 1 };
+enum { ERR_UNSUPPORTED_BLOCK = 1, ERR_MIXER_ALIAS = 2 };
 
 // ---------------------------------------------------------------- sub-model state blocks
 struct MatchM {   // MatchModel (:3520-3693)

@@ -14,6 +14,7 @@
 #pragma once
 #include "exact_math.h"
 #include "state.h"
+#include "bytemodel.cuh"
 
 namespace cmixb200 {
 
@@ -69,22 +70,6 @@ __device__ __forceinline__ float stretch(const Tables& T, float p) {     // mixe
   int index = (int)XM_FMUL(p, 100001.0f);
   if (index >= 100001) index = 100000; else if (index < 0) index = 0;
   return T.logit[index];
-}
-
-// ByteModel::Predict (byte-model.cpp:8-24): sequential range sums, first-max argmax.
-__device__ float bytemodel_predict(const float* probs, int bot, int top, int* ex_out) {
-  const int m = bot + ((top - bot) / 2);
-  float num = 0.0f;
-#pragma unroll 8
-  for (int i = m + 1; i <= top; ++i) num = XM_FADD(num, probs[i]);
-  float denom = num;
-#pragma unroll 8
-  for (int i = bot; i <= m; ++i) denom = XM_FADD(denom, probs[i]);
-  int ex = bot; float best = probs[bot];
-  for (int i = bot + 1; i <= top; ++i) if (probs[i] > best) { best = probs[i]; ex = i; }
-  if (ex_out) *ex_out = ex;
-  if (denom == 0) return 0.5f;
-  return XM_FDIV(num, denom);
 }
 
 struct SmallShared {
