@@ -368,7 +368,14 @@ int BuildFxcm(cmixb200_predictor* P) {
     T->dict_chars = d_chars; T->dict_off = d_off; T->dict_n = (int)D.off.size(); T->dict_loaded = 1;
   }
   TRY(P->Alloc(&P->d_fx_tables, 1, false));
-  CK(cudaMemcpy(P->d_fx_tables, T, sizeof *T, cudaMemcpyHostToDevice));
+  {
+    fx::Tables* up = new fx::Tables(*T);               // the device copy's table pointers address the device copy
+    up->map = reinterpret_cast<const fx::MapTab*>(reinterpret_cast<const u8*>(P->d_fx_tables) + offsetof(fx::Tables, map_store));
+    up->st2 = reinterpret_cast<const short (*)[4096]>(reinterpret_cast<const u8*>(P->d_fx_tables) + offsetof(fx::Tables, st2_store));
+    const cudaError_t ce = cudaMemcpy(P->d_fx_tables, up, sizeof *up, cudaMemcpyHostToDevice);
+    delete up;
+    CK(ce);
+  }
   fx::State* S = new fx::State();
   fx::TextState* X = new fx::TextState();
   DeviceBackend be{P};

@@ -90,6 +90,7 @@ inline void fill_digits(u8* dst, int n, const char* hex) {
 // Fill every field of T except the dictionary pointers.
 inline void build_tables(Tables& T) {
   memset(&T, 0, sizeof T);
+  T.map = T.map_store; T.st2 = T.st2_store;
   // squash / stretch (fxcmv1.cpp:137-175): float/double mix exactly as written there
   for (int d = -2047; d <= 2047; ++d) {
     float p = 1.0f / (1.0f + exp(-d / 256.0));
@@ -121,9 +122,9 @@ inline void build_tables(Tables& T) {
     delete g;
   }
   for (int i = 0; i < 4096; ++i) {
-    T.st2[0][i] = 0;
-    T.st2[1][i] = (short)clp(host_sc(12 * (i - 2048)));
-    T.st2[2][i] = (short)clp(host_sc(14 * (i - 2048)));
+    T.st2_store[0][i] = 0;
+    T.st2_store[1][i] = (short)clp(host_sc(12 * (i - 2048)));
+    T.st2_store[2][i] = (short)clp(host_sc(14 * (i - 2048)));
   }
   for (int r = 0; r < 256; ++r) {   // RunContextMap::Init(m, 6) (fxcmv1.cpp:765-777)
     int c = T.ilog[r] * 8;
@@ -138,7 +139,7 @@ inline void build_tables(Tables& T) {
   for (int id = 0; id < N_MAPS; ++id) {   // ContextMap::Init table part (fxcmv1.cpp:1000-1043)
     const MapSpec sp = kMapSpec[id];
     T.spec[id] = sp;
-    MapTab& mt = T.map[id];
+    MapTab& mt = T.map_store[id];
     const u8* nn = T.sta[sp.sta];
     const int cmul = (int)c_r[sp.par], cms = (int)c_s[sp.par], cms3 = (int)c_s3[sp.par], cms4 = (int)c_s4[sp.par];
     for (int rc = 0; rc < 256; ++rc) {

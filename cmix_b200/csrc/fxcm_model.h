@@ -21,6 +21,8 @@
 #ifndef CMIXB200_FXCM_MODEL_H
 #define CMIXB200_FXCM_MODEL_H
 
+#include <stddef.h>
+
 #include "fxcm_text.h"
 
 namespace cmixb200 {
@@ -68,9 +70,7 @@ struct Tables {
   u8 ilog[256];
   int dt[1024];
   u8 sta[6][1024];       // six generated bit-history state tables (:241-357), [state*4 + {next0, next1, n0, n1}]
-  short st2[3][4096];
   short rcm_rc[512];
-  MapTab map[N_MAPS];
   MapSpec spec[N_MAPS];
   int mix_m[N_MIX], mix_shift[N_MIX], mix_uperr[N_MIX];
   u8 wrt2[256], wrt3[256], wrt4[256];   // byte classes (fxcmv1.cpp:51-90, :1843-1862)
@@ -79,7 +79,14 @@ struct Tables {
   int e_l[8];
   const char* dict_chars; const u32* dict_off;   // WRT dictionary words, NUL terminated (:398-410)
   int dict_n, dict_loaded;
+  // the big per-map tables stay out of line: everything above map_store can be staged in shared memory (TABLES_HOT_BYTES)
+  const MapTab* map;                    // -> map_store
+  const short (*st2)[4096];             // -> st2_store
+  alignas(16) MapTab map_store[N_MAPS];
+  short st2_store[3][4096];
 };
+enum { TABLES_HOT_BYTES = offsetof(Tables, map_store) };
+static_assert(TABLES_HOT_BYTES % 16 == 0, "the hot part of the tables is copied in 16-byte words");
 
 // ---------------------------------------------------------------- mutable state of one stream
 struct MapState {
@@ -133,7 +140,7 @@ struct State {
   int ord_x, ord_w, is_match;
   int lstmpr, lstmex;
   // vectors
-  short in1[N_IN1 + 48];
+  alignas(16) short in1[N_IN1 + 48];
   short in2[N_IN2];
   u16 codes[N_OUT + 1];  // exported 12-bit codes, 0xFFFF = slot still holds 0.5
   int in_off[N_UNITS + 1], ex_off[N_UNITS + 1];
@@ -207,8 +214,45 @@ FX_HD inline void map_set(MapState& m, u32 cx) {   // ContextMap::set (fxcmv1.cp
 }
 FX_HD inline void map_skip(MapState& m) { m.cn++; m.mask = (u16)(m.mask + 1); m.mask = (u16)(m.mask * 2); }
 
-// One bit of one context map: train the cells with y, move to the next cells, emit the inputs (mix / mix1).
-FX_HD inline void map_bit(State& S, int id, Out& o) {
+// Read-only probe of E<A,B>::get: which slot of the bucket at `base` holds checksum ch (-1: get would replace one).
+FX_HD inline int bucket_peek(const u8* t, u32 base, int A, u16 ch) {
+  const u8* e = t + base;
+  const u16* chk = reinterpret_cast<const u16*>(e);
+  const u8 last = e[2 * A];
+  if (chk[last & 15] == ch) return last & 15;
+  for (int i = 0; i < A; ++i) if (chk[i] == ch) return i;
+  return -1;
+}
+// The buckets context i of map `id` reads or writes this bit (at most 5): its live cell's, its run-info cell's, the one it moves
+// to and, on a byte boundary, the two of a deferred history write-back. A skipped context touches none.
+FX_HD inline int map_touched(const State& S, int id, int i, u32* ids) {
+  const Tables& T = *S.T;
+  const MapState& m = S.map[id];
+  const MapSpec sp = T.spec[id];
+  const int A = map_slots(sp.kind), sh = map_shift(sp.kind);
+  const int bp = S.bpos;
+  if ((m.mask >> (m.cn - i)) & 1) return 0;
+  int n = 0;
+  if (m.cp[i] != FX_NULL) ids[n++] = m.cp[i] >> sh;
+  ids[n++] = m.runp[i] >> sh;
+  if (bp > 1 && m.t[m.runp[i]] == 0) return n;
+  if (bp == 0 || bp == 2 || bp == 5) {
+    const u32 b = (m.cxt[i] + (u32)S.c0) & m.tmask;
+    ids[n++] = b;
+    if (bp == 0) {
+      const u16 chk = (u16)((m.cxt[i] >> 16) ^ i);
+      const int slot = bucket_peek(m.t, b << sh, A, chk);
+      if (slot >= 0) {
+        const u8* cell0 = m.t + (b << sh) + 2 * A + 1 + 7 * slot;
+        if (cell0[3] == 2) { const int c = cell0[4] + 256; ids[n++] = (m.cxt[i] + (u32)(c >> 6)) & m.tmask; ids[n++] = (m.cxt[i] + (u32)(c >> 3)) & m.tmask; }
+      }
+    }
+  }
+  return n;
+}
+// One bit of one context of one map: train the cell with y, move to the next cell, emit the inputs (mix / mix1) at the
+// context's own slice of the unit's inputs / exports. Returns 1 when the context has a non-zero state.
+FX_HD inline u32 map_ctx_bit(State& S, int id, int i, const Out& unit) {
   const Tables& T = *S.T;
   MapState& m = S.map[id];
   const MapSpec sp = T.spec[id];
@@ -218,61 +262,72 @@ FX_HD inline void map_bit(State& S, int id, Out& o) {
   const int A = map_slots(sp.kind), sh = map_shift(sp.kind);
   const int y = S.y, bp = S.bpos, cc = S.c0;
   const u8 c1 = (u8)S.c4;
-  u32 result = 0;
-  for (int i = 0; i < m.cn; ++i) {
-    if ((m.mask >> (m.cn - i)) & 1) {   // skipped context: constant inputs
-      emit(T, o, 0); if (sp.skip2) emit(T, o, 0); emit(T, o, 0); emit(T, o, 0); emit(T, o, 64, false); emit(T, o, 0);
-      continue;
-    }
-    if (m.cp[i] != FX_NULL) m.t[m.cp[i]] = nn[m.t[m.cp[i]] * 4 + y];
-    int s = 0;
-    if (bp > 1 && m.t[m.runp[i]] == 0) m.cp[i] = FX_NULL;
-    else {
-      const u16 chk = (u16)((m.cxt[i] >> 16) ^ i);
-      if (bp) {
-        if (bp == 2 || bp == 5) m.cp0[i] = m.cp[i] = bucket_get(m.t, ((m.cxt[i] + cc) & m.tmask) << sh, A, chk, sp.kep);
-        else m.cp[i] = m.cp0[i] + state_byte_location(bp, cc);
-      } else {
-        m.cp0[i] = m.cp[i] = bucket_get(m.t, ((m.cxt[i] + cc) & m.tmask) << sh, A, chk, sp.kep);
-        if (m.t[m.cp0[i] + 3] == 2) {   // deferred bit histories of bits 2-7 for a context seen the second time
-          const int c = m.t[m.cp0[i] + 4] + 256;
-          u32 p = bucket_get(m.t, ((m.cxt[i] + (c >> 6)) & m.tmask) << sh, A, chk, sp.kep);
-          m.t[p] = (u8)(1 + ((c >> 5) & 1));
-          m.t[p + 1 + ((c >> 5) & 1)] = (u8)(1 + ((c >> 4) & 1));
-          m.t[p + 3 + ((c >> 4) & 3)] = (u8)(1 + ((c >> 3) & 1));
-          p = bucket_get(m.t, ((m.cxt[i] + (c >> 3)) & m.tmask) << sh, A, chk, sp.kep);
-          m.t[p] = (u8)(1 + ((c >> 2) & 1));
-          m.t[p + 1 + ((c >> 2) & 1)] = (u8)(1 + ((c >> 1) & 1));
-          m.t[p + 3 + ((c >> 1) & 3)] = (u8)(1 + (c & 1));
-          m.t[m.cp0[i] + 6] = 0;
-        }
-        u8* rp = m.t + m.runp[i];
-        if (rp[0] == 0) { rp[0] = 2; rp[1] = c1; }
-        else if (rp[1] != c1) { rp[0] = 1; rp[1] = c1; }
-        else if (rp[0] < 254) rp[0] += 2;
-        m.runp[i] = m.cp0[i] + 3;
-      }
-      s = m.t[m.cp[i]];
-    }
-    if (s == 0) {
-      emit(T, o, 0); if (sp.skip2) emit(T, o, 0); emit(T, o, 0); emit(T, o, 0); emit(T, o, 64, false);
-    } else {
-      u32* sm = m.sm + i * 256;          // StateMap::set (fxcmv1.cpp:686-704)
-      u32 p0 = sm[m.sm_cxt[i]];
-      p0 += (u32)((y << 19) - (int)(p0 >> 13));
-      sm[m.sm_cxt[i]] = p0;
-      m.sm_cxt[i] = (u32)s;
-      const int p1 = (int)(sm[s] >> 20);
-      emit(T, o, tab.st1[p1]); if (sp.skip2) emit(T, o, st2[p1]); emit(T, o, tab.st8[s]); emit(T, o, tab.st32[s]); emit(T, o, 0, false);
-      ++result;
-    }
-    const u8* rp = m.t + m.runp[i];
-    int b = S.c0shift_bpos ^ (rp[1] >> S.bposshift);
-    if (b <= 1) emit(T, o, tab.rc1[rp[0] + b * 256]);
-    else emit(T, o, 0);
+  Out o = unit;
+  o.ni += i * (5 + sp.skip2); o.ei += i * (4 + sp.skip2);
+  if ((m.mask >> (m.cn - i)) & 1) {   // skipped context: constant inputs
+    emit(T, o, 0); if (sp.skip2) emit(T, o, 0); emit(T, o, 0); emit(T, o, 0); emit(T, o, 64, false); emit(T, o, 0);
+    return 0;
   }
-  if (bp == 7) { m.cn = 0; m.mask = 0; }
+  u32 result = 0;
+  if (m.cp[i] != FX_NULL) m.t[m.cp[i]] = nn[m.t[m.cp[i]] * 4 + y];
+  int s = 0;
+  if (bp > 1 && m.t[m.runp[i]] == 0) m.cp[i] = FX_NULL;
+  else {
+    const u16 chk = (u16)((m.cxt[i] >> 16) ^ i);
+    if (bp) {
+      if (bp == 2 || bp == 5) m.cp0[i] = m.cp[i] = bucket_get(m.t, ((m.cxt[i] + cc) & m.tmask) << sh, A, chk, sp.kep);
+      else m.cp[i] = m.cp0[i] + state_byte_location(bp, cc);
+    } else {
+      m.cp0[i] = m.cp[i] = bucket_get(m.t, ((m.cxt[i] + cc) & m.tmask) << sh, A, chk, sp.kep);
+      if (m.t[m.cp0[i] + 3] == 2) {   // deferred bit histories of bits 2-7 for a context seen the second time
+        const int c = m.t[m.cp0[i] + 4] + 256;
+        u32 p = bucket_get(m.t, ((m.cxt[i] + (c >> 6)) & m.tmask) << sh, A, chk, sp.kep);
+        m.t[p] = (u8)(1 + ((c >> 5) & 1));
+        m.t[p + 1 + ((c >> 5) & 1)] = (u8)(1 + ((c >> 4) & 1));
+        m.t[p + 3 + ((c >> 4) & 3)] = (u8)(1 + ((c >> 3) & 1));
+        p = bucket_get(m.t, ((m.cxt[i] + (c >> 3)) & m.tmask) << sh, A, chk, sp.kep);
+        m.t[p] = (u8)(1 + ((c >> 2) & 1));
+        m.t[p + 1 + ((c >> 2) & 1)] = (u8)(1 + ((c >> 1) & 1));
+        m.t[p + 3 + ((c >> 1) & 3)] = (u8)(1 + (c & 1));
+        m.t[m.cp0[i] + 6] = 0;
+      }
+      u8* rp = m.t + m.runp[i];
+      if (rp[0] == 0) { rp[0] = 2; rp[1] = c1; }
+      else if (rp[1] != c1) { rp[0] = 1; rp[1] = c1; }
+      else if (rp[0] < 254) rp[0] += 2;
+      m.runp[i] = m.cp0[i] + 3;
+    }
+    s = m.t[m.cp[i]];
+  }
+  if (s == 0) {
+    emit(T, o, 0); if (sp.skip2) emit(T, o, 0); emit(T, o, 0); emit(T, o, 0); emit(T, o, 64, false);
+  } else {
+    u32* sm = m.sm + i * 256;          // StateMap::set (fxcmv1.cpp:686-704)
+    u32 p0 = sm[m.sm_cxt[i]];
+    p0 += (u32)((y << 19) - (int)(p0 >> 13));
+    sm[m.sm_cxt[i]] = p0;
+    m.sm_cxt[i] = (u32)s;
+    const int p1 = (int)(sm[s] >> 20);
+    emit(T, o, tab.st1[p1]); if (sp.skip2) emit(T, o, st2[p1]); emit(T, o, tab.st8[s]); emit(T, o, tab.st32[s]); emit(T, o, 0, false);
+    result = 1;
+  }
+  const u8* rp = m.t + m.runp[i];
+  int b = S.c0shift_bpos ^ (rp[1] >> S.bposshift);
+  if (b <= 1) emit(T, o, tab.rc1[rp[0] + b * 256]);
+  else emit(T, o, 0);
+  return result;
+}
+FX_HD inline void map_finish(State& S, int id, u32 result) {
+  MapState& m = S.map[id];
+  if (S.bpos == 7) { m.cn = 0; m.mask = 0; }
   m.result = result;
+}
+// One bit of one context map, contexts in order (mix / mix1).
+FX_HD inline void map_bit(State& S, int id, Out& o) {
+  u32 result = 0;
+  const int cn = S.map[id].cn;
+  for (int i = 0; i < cn; ++i) result += map_ctx_bit(S, id, i, o);
+  map_finish(S, id, result);
 }
 
 // ---------------------------------------------------------------- small units
@@ -1065,7 +1120,7 @@ FX_HD inline void bit_train(State& S, int lane, int lanes) {
   }
 }
 // Phase C (one lane): failure history, then (byte boundary) the text analysis, then the units' slices of the vectors.
-FX_HD inline void bit_prepare(State& S) {
+FX_HD inline void bit_prepare_head(State& S) {
   const Tables& T = *S.T;
   if (S.fails & 0x00000080) --S.failcount;
   S.fails = S.fails * 2;
@@ -1077,14 +1132,22 @@ FX_HD inline void bit_prepare(State& S) {
   S.pr = pr;
   if (S.bpos == 0) text_byte(S);
   S.ord_x = S.map[M2_0].mask ? 2 : 0;      // cmC2[0].cxtMask is sampled before its mix() (fxcmv1.cpp:4590-4591)
+}
+FX_HD inline void unit_counts(const State& S, int u, int& ni, int& ei) {   // inputs / exports of unit u this bit
+  if (u < U_MATCH) { ni = 2; ei = 1; }
+  else if (u == U_MATCH) { ni = 7; ei = 7; }
+  else if (u == U_SMATCH) { ni = 2; ei = 2; }
+  else if (u == U_RCM) { ni = 1; ei = 1; }
+  else { const int id = u - U_MAP0; const int k = S.T->spec[id].skip2; ni = S.map[id].cn * (5 + k); ei = S.map[id].cn * (4 + k); }
+}
+FX_HD inline void bit_prepare(State& S) {
+  bit_prepare_head(S);
   int ni = 0, ei = 0;
   for (int u = 0; u < N_UNITS; ++u) {
     S.in_off[u] = ni; S.ex_off[u] = ei;
-    if (u < U_MATCH) { ni += 2; ei += 1; }
-    else if (u == U_MATCH) { ni += 7; ei += 7; }
-    else if (u == U_SMATCH) { ni += 2; ei += 2; }
-    else if (u == U_RCM) { ni += 1; ei += 1; }
-    else { const int id = u - U_MAP0; const int k = T.spec[id].skip2; ni += S.map[id].cn * (5 + k); ei += S.map[id].cn * (4 + k); }
+    int a, b;
+    unit_counts(S, u, a, b);
+    ni += a; ei += b;
   }
   S.in_off[N_UNITS] = ni; S.ex_off[N_UNITS] = ei;
 }

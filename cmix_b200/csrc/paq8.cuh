@@ -44,14 +44,16 @@ __device__ unsigned long long g_p8_prof[2][64];
 #define P8_M(slot) do { } while (0)
 #define P8_C(slot, n) do { } while (0)
 #endif
-enum { P8_THREADS = 384, P8_WARPS = 12, P8_N_CM = 16, P8_N_CM2 = 3, P8_CM_LANES = 210, P8_CM2_LANES = 63, P8_N_UNITS = 53,
+enum { P8_THREADS = 512, P8_WARPS = 16, P8_MAP_THREADS = 384, P8_MAP_WARPS = 12, P8_SGD_THREADS = 128, P8_N_CM = 16, P8_N_CM2 = 3, P8_CM_LANES = 210, P8_CM2_LANES = 63, P8_N_UNITS = 53,
        P8_CM2_TID0 = 224, P8_TID_PIC = 287, P8_TID_MATCH = 288, P8_TID_W10 = 320, P8_TID_W11 = 352 };
 
 struct P8Shared {
   p8::State S;
   alignas(16) short wc[p8::N_SETS][p8::N_IN];   // the weight sets of the pending prediction (slot i holds set wc_set[i])
   alignas(16) unsigned char tab[p8::TABLES_HOT_BYTES];
+  alignas(16) short tx_old[p8::N_IN];           // the inputs of the previous bit: the SGD warps train while the map warps write new ones
   int wc_set[p8::N_SETS];
+  int sgd_err[p8::N_SETS], sgd_nx, sgd_ncxt;
   int unit_off[P8_N_UNITS + 1];
   // pass-1 results of the 7-slot maps
   short ns[P8_CM_LANES];
@@ -282,36 +284,27 @@ __device__ __forceinline__ void p8_probe_single(P8Shared& sh, int tid, int y, in
   using namespace p8;
   State& S = sh.S;
   const p8::Tables& T = *S.T;
-  if (tid == P8_TID_PIC) { Out o = p8_out(sh, sh.unit_off[19]); pic_bit(S, o); }
-  else if (tid == P8_TID_MATCH) { Out o = p8_out(sh, sh.unit_off[7]); match_bit(S, o); }
+  if (tid == P8_TID_PIC) pic_core(S);
+  else if (tid == P8_TID_MATCH) { Out o = p8_out(sh, sh.unit_off[7]); match_core(S, o); }
+  else if (tid == P8_TID_MATCH + 1) { if (bpos != 0) record_pre(S); }   // on a byte boundary it follows record_byte (p8_number)
   else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 10) sh.dmc_st[tid - P8_TID_W10] = dmc_st(T, S.dmc[tid - P8_TID_W10], y);
   else if (tid >= P8_TID_W10 + 10 && tid < P8_TID_W10 + 13) {
     const int r = tid - (P8_TID_W10 + 10);
     Out o = p8_out(sh, sh.unit_off[4 + r]);
     rcm_mix(r == 0 ? S.rcm7 : r == 1 ? S.rcm9 : S.rcm10, o, c0, bpos);
   } else if (tid >= P8_TID_W10 + 13 && tid < P8_TID_W10 + 18) { const int r = tid - (P8_TID_W10 + 13); Out o = p8_out(sh, sh.unit_off[48 + r]); linear_small(S, o, r); }
-  else if (tid == P8_TID_W11) { Out o = p8_out(sh, sh.unit_off[8]); smatch_core(S, o); }
-  else if (tid == P8_TID_W11 + 1) {
-    Out o = p8_out(sh, sh.unit_off[0]);
-    add(o, 64);
-    add(o, (stretch(T, sm32_p(T, S.sm0, y, c0)) + 1) >> 1);
-    add(o, (stretch(T, sm32_p(T, S.sm1, y, c0 | (buf(S, 1) << 8))) + 1) >> 1);
-  }
+  else if (tid == P8_TID_W11) { Out o = p8_out(sh, sh.unit_off[8]); smatch_head(S, o); }
+  else if (tid == P8_TID_W11 + 1 || tid == P8_TID_W11 + 2) {
+    const int r = tid - (P8_TID_W11 + 1);
+    Out o = p8_out(sh, sh.unit_off[1 + r]);
+    add(o, (stretch(T, sm32_p(T, r == 0 ? S.sm0 : S.sm1, y, r == 0 ? c0 : (c0 | (buf(S, 1) << 8)))) + 1) >> 1);
+  } else if (tid == P8_TID_W11 + 3) { Out o = p8_out(sh, sh.unit_off[0]); add(o, 64); }
 }
-// between the passes: DMC forest combination (dmcForest::mix), the record model's per-bit contexts, the draws
+// between the passes: the record model's per-bit contexts on a byte boundary, the draws
 __device__ __forceinline__ void p8_number(P8Shared& sh, int tid, int y, int c0, int bpos) {
   using namespace p8;
   State& S = sh.S;
-  if (tid == P8_TID_W10) {
-    Out o = p8_out(sh, sh.unit_off[44]);
-    const u32 params[10] = {2, 32, 64, 4, 128, 8, 256, 16, 1024, 1536};
-    add(o, sh.dmc_st[9] >> 3);
-    add(o, sh.dmc_st[8] >> 3);
-    for (int i = 7; i > 0; i -= 2) add(o, (sh.dmc_st[i] + sh.dmc_st[i - 1]) >> 4);
-    if (bpos == 0)
-      for (int i = 7; i >= 0; --i)
-        if ((S.dmc[i].extra >> 7) > S.dmc[i].size) dmc_reset(S.dmc[i], params[i]);
-  } else if (tid == P8_TID_W11) record_pre(S);
+  if (tid == P8_TID_W11) { if (bpos == 0) record_pre(S); }
   else if (tid < 32) {
     const unsigned full = 0xffffffffu;
     const int lane = tid;
@@ -377,14 +370,33 @@ __device__ __forceinline__ void p8_apply_cm(P8Shared& sh, int tid, int y, int c0
   Out o = p8_out(sh, sh.unit_off[c_p8_cm_unit[k]] + 5 * i);
   cm_step(m, i, o, ns, y, c0, bpos, buf(sh.S, 1));
 }
-__device__ __forceinline__ void p8_apply_small(P8Shared& sh, int tid, int y) {
+__device__ __forceinline__ void p8_apply_small(P8Shared& sh, int tid, int y, int bpos) {
   using namespace p8;
-  if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 12) {   // the record model's 12 direct maps (contexts selected by record_pre)
+  State& S = sh.S;
+  if (tid >= P8_TID_MATCH && tid < P8_TID_MATCH + 9) {   // the nine maps behind the match model
+    Out o = p8_out(sh, sh.unit_off[7]);
+    match_unit(S, o, tid - P8_TID_MATCH);
+  } else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 12) {   // the record model's 12 direct maps (contexts selected by record_pre)
     Out o = p8_out(sh, sh.unit_off[24 + (tid - P8_TID_W10)]);
-    record_small(sh.S, o, tid - P8_TID_W10);
+    record_small(S, o, tid - P8_TID_W10);
+  } else if (tid == P8_TID_W10 + 12) {                     // DMC forest combination and reset (dmcForest::mix)
+    Out o = p8_out(sh, sh.unit_off[44]);
+    const u32 params[10] = {2, 32, 64, 4, 128, 8, 256, 16, 1024, 1536};
+    add(o, sh.dmc_st[9] >> 3);
+    add(o, sh.dmc_st[8] >> 3);
+    for (int i = 7; i > 0; i -= 2) add(o, (sh.dmc_st[i] + sh.dmc_st[i - 1]) >> 4);
+    if (bpos == 0)
+      for (int i = 7; i >= 0; --i)
+        if ((S.dmc[i].extra >> 7) > S.dmc[i].size) dmc_reset(S.dmc[i], params[i]);
   } else if (tid >= P8_TID_W11 && tid < P8_TID_W11 + 7) {   // sparseModel1's seven stationary maps
     Out o = p8_out(sh, sh.unit_off[11 + (tid - P8_TID_W11)]);
-    scm_mix(sh.S.sparse1.scm[tid - P8_TID_W11], o, y);
+    scm_mix(S.sparse1.scm[tid - P8_TID_W11], o, y);
+  } else if (tid >= P8_TID_W11 + 7 && tid < P8_TID_W11 + 11) {
+    Out o = p8_out(sh, sh.unit_off[8]);
+    smatch_unit(S, o, tid - (P8_TID_W11 + 7));
+  } else if (tid >= P8_TID_W11 + 11 && tid < P8_TID_W11 + 14) {
+    Out o = p8_out(sh, sh.unit_off[19]);
+    pic_unit(S, o, tid - (P8_TID_W11 + 11));
   }
 }
 
@@ -462,7 +474,32 @@ __device__ __forceinline__ void p8_row_store(short* dst, const short* src, int l
 }
 static_assert(p8::N_IN % 8 == 0 && p8::N_IN / 8 <= 7 * 32, "a weight row is at most 7 16-byte words per lane");
 
-// One bit: PAQ8::Perceive(y). All P8_THREADS lanes call it.
+__device__ __forceinline__ void p8_sync_maps() { asm volatile("bar.sync 1, 384;" ::: "memory"); static_assert(P8_MAP_THREADS == 384, "named barrier width"); }
+
+// Mixer::update for the 28 cached weight sets selected for the previous bit, by the four SGD warps (tid 0..127 of them)
+__device__ __forceinline__ void p8_sgd(P8Shared& sh, int t) {
+  using namespace p8;
+  const int n8 = sh.sgd_nx >> 3, total = sh.sgd_ncxt * n8;
+  if (n8 == 0) return;
+  int i = t / n8, q = t - i * n8;
+  for (int idx = t; idx < total; idx += P8_SGD_THREADS) {
+    const int err = sh.sgd_err[i];
+    if (err) {
+      uint4* wp = reinterpret_cast<uint4*>(&sh.wc[i][q * 8]);
+      uint4 wv = *wp;
+      const uint4 xv = *reinterpret_cast<const uint4*>(&sh.tx_old[q * 8]);
+      short* w = reinterpret_cast<short*>(&wv);
+      const short* x = reinterpret_cast<const short*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = train_one(x[e], w[e], err);
+      *wp = wv;
+    }
+    q += P8_SGD_THREADS;
+    while (q >= n8) { q -= n8; ++i; }
+  }
+}
+
+// One bit: PAQ8::Perceive(y). All P8_THREADS lanes call it: warps 0-11 evaluate the models, warps 12-15 train the mixer beside them.
 __device__ void p8_bit(P8Shared& sh, int y, int tid) {
   using namespace p8;
   State& S = sh.S;
@@ -471,37 +508,27 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
 #ifdef P8_PROF
   if (tid == 0) { sh.prof_t = clock64(); sh.prof_row = (S.bpos == 7) ? 0 : 1; }   // bpos before bit_begin: 7 -> this bit starts a byte
 #endif
-  // ---- phase 0: bookkeeping
+  // ---- phase 0: bookkeeping; the previous bit's inputs and errors move aside for the SGD warps
   if (tid == 0) {
+    sh.sgd_nx = S.m.nx; sh.sgd_ncxt = S.m.ncxt;
     bit_begin(S, y);
     if (S.bpos == 0) block_parse(S);
     sh.snap_spaces = S.spaces; sh.snap_words = S.words; sh.snap_frstchar = S.frstchar; sh.snap_spafdo = S.spafdo;
   }
   if (tid >= 32 && tid < 32 + P8_N_CM) sh.clash[tid - 32] = 0;
   if (tid >= 64 && tid < 64 + P8_N_CM2) { sh.clash2[tid - 64] = 0; sh.res2[tid - 64] = 0; }
+  if (tid >= 96 && tid < 96 + N_SETS) sh.sgd_err[tid - 96] = ((y << 12) - S.m.pr[tid - 96]) * 7;
+  if (tid >= 128 && tid < 128 + N_IN / 8) reinterpret_cast<uint4*>(sh.tx_old)[tid - 128] = reinterpret_cast<const uint4*>(S.m.tx)[tid - 128];
   for (int k = tid; k < P8_SEEN; k += P8_THREADS) sh.u.seen[k] = 0ull;
   __syncthreads();
   P8_T(0);
   const int bpos = S.bpos, c0 = S.c0;
   const bool byte_start = bpos == 0;
-  // ---- phase 1: SGD on the 28 cached weight sets selected for the previous bit (Mixer::update); mixer-input offsets of the units
-  {
-    Mixer& m = S.m;
-    const int n8 = m.nx >> 3, total = m.ncxt * n8;
-    for (int idx = tid; idx < total; idx += P8_THREADS) {
-      const int i = idx / n8, q = idx - i * n8;
-      const int err = ((y << 12) - m.pr[i]) * 7;
-      if (!err) continue;
-      uint4* wp = reinterpret_cast<uint4*>(&sh.wc[i][q * 8]);
-      uint4 wv = *wp;
-      const uint4 xv = *reinterpret_cast<const uint4*>(&m.tx[q * 8]);
-      short* w = reinterpret_cast<short*>(&wv);
-      const short* x = reinterpret_cast<const short*>(&xv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) w[e] = train_one(x[e], w[e], err);
-      *wp = wv;
-    }
-    if (warp == P8_WARPS - 1) {           // unit offsets: two units per lane, prefix over the warp
+  if (tid >= P8_MAP_THREADS) p8_sgd(sh, tid - P8_MAP_THREADS);
+  else {
+    // ---- mixer-input offsets of the units, history-map prologues
+    if (tid == 0) { S.m.nx = S.m.base = S.m.ncxt = 0; }
+    if (warp == P8_MAP_WARPS - 1) {           // two units per lane, prefix over the warp
       const unsigned full = 0xffffffffu;
       const int a = p8_unit_count(S, lane, byte_start);
       const int b = lane + 32 < P8_N_UNITS ? p8_unit_count(S, lane + 32, byte_start) : 0;
@@ -516,102 +543,101 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
       if (lane + 32 <= P8_N_UNITS) sh.unit_off[lane + 32] = ta + ib - b;
     }
     if (tid >= P8_CM2_TID0 && tid < P8_CM2_TID0 + P8_N_CM2) cm2_begin(p8_cm2(S, tid - P8_CM2_TID0), y, bpos);
-  }
-  __syncthreads();
-  P8_T(1);
-  if (tid == 0) { S.m.nx = S.m.base = S.m.ncxt = 0; }
-  if (byte_start) {
-    // ---- byte boundary, round 1: context computation, one model per lane / warp
-    {
-      P8_M0;
-      if (warp < 3) p8_ols_byte_warp(sh, warp, lane);
-      else if (lane == 0) {
-        switch (warp) {
-          case 3: ordern_byte(S); break;
-          case 4: distance_byte(S); record1_byte(S); break;
-          case 5: word_byte(S); break;
-          case 6: nest_byte(S); indirect_byte(S); break;
-          case 7: xml_byte(S); break;
-          case 8: text_update(S); text_contexts(S); break;
-          case 9: exe_byte(S); break;
-          case 10: {
-            const u8 W = (u8)buf(S, 1), WW = (u8)buf(S, 2), WWW = (u8)buf(S, 3);
-            S.linear.prd[3] = (u8)clip8(W * 2 - WW);
-            S.linear.prd[4] = (u8)clip8(W * 3 - WW * 3 + WWW);
-          } break;
+    if (byte_start) {
+      // ---- byte boundary, round 1: context computation, one model per lane / warp
+      {
+        P8_M0;
+        if (warp < 3) p8_ols_byte_warp(sh, warp, lane);
+        else if (lane == 0) {
+          switch (warp) {
+            case 3: ordern_byte(S); break;
+            case 4: distance_byte(S); record1_byte(S); break;
+            case 5: word_byte(S); break;
+            case 6: nest_byte(S); indirect_byte(S); break;
+            case 7: xml_byte(S); break;
+            case 8: text_update(S); text_contexts(S); break;
+            case 9: exe_byte(S); break;
+            case 10: {
+              const u8 W = (u8)buf(S, 1), WW = (u8)buf(S, 2), WWW = (u8)buf(S, 3);
+              S.linear.prd[3] = (u8)clip8(W * 2 - WW);
+              S.linear.prd[4] = (u8)clip8(W * 3 - WW * 3 + WWW);
+            } break;
+          }
         }
+        if (lane == 0) P8_M(24 + warp);
       }
-      if (lane == 0) P8_M(24 + warp);
+      p8_sync_maps();
+      P8_T(2);
+      for (int k = tid; k < P8_SEEN; k += P8_MAP_THREADS) sh.u.seen[k] = 0ull;   // the OLS warps used this memory
+      p8_sync_maps();
+      // ---- the history maps and the single-lane units
+      p8_probe_cm2(sh, tid, bpos);
+      p8_probe_single(sh, tid, y, c0, bpos);
+      p8_sync_maps();
+      P8_T(3);
+      p8_apply_cm2(sh, tid, y, bpos);
+      p8_sync_maps();
+      P8_T(4);
+      // ---- round 2 of the byte boundary (needs the order-N result and the match model)
+      {
+        const int ismatch = ilog(T, S.match.length);
+        if (tid == 32) sparse_byte(S, ismatch, sh.res2[0]);
+        else if (tid == 64) {
+          // sparseModel1 runs BEFORE wordModel in the reference: it sees the previous byte's word statistics
+          const u32 a = S.spaces, b = S.words, c = S.frstchar, d = S.spafdo;
+          S.spaces = sh.snap_spaces; S.words = sh.snap_words; S.frstchar = sh.snap_frstchar; S.spafdo = sh.snap_spafdo;
+          sparse1_byte(S, ismatch, sh.res2[0]);
+          S.spaces = a; S.words = b; S.frstchar = c; S.spafdo = d;
+        } else if (tid == 96) record_byte(S);
+      }
+      for (int k = tid; k < P8_SEEN; k += P8_MAP_THREADS) sh.u.seen[k] = 0ull;
+      p8_sync_maps();
+      P8_T(5);
+      if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
+      p8_sync_maps();
+      P8_T(6);
+      p8_number(sh, tid, y, c0, bpos);
+      p8_sync_maps();
+      P8_T(7);
+      p8_apply_cm(sh, tid, y, c0, bpos);
+      p8_apply_small(sh, tid, y, bpos);
+      p8_sync_maps();
+      P8_T(8);
+    } else {
+      p8_sync_maps();
+      P8_T(1);
+      // ---- inside a byte: probe / number / apply, all map families side by side
+      if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
+      else { p8_probe_cm2(sh, tid, bpos); p8_probe_single(sh, tid, y, c0, bpos); }
+      p8_sync_maps();
+      P8_T(3);
+      p8_number(sh, tid, y, c0, bpos);
+      p8_sync_maps();
+      P8_T(7);
+      if (warp < 7) p8_apply_cm(sh, tid, y, c0, bpos);
+      else { p8_apply_cm2(sh, tid, y, bpos); p8_apply_small(sh, tid, y, bpos); }
+      p8_sync_maps();
+      P8_T(8);
     }
-    __syncthreads();
-    P8_T(2);
-    for (int k = tid; k < P8_SEEN; k += P8_THREADS) sh.u.seen[k] = 0ull;   // the OLS warps used this memory
-    __syncthreads();
-    // ---- the history maps and the single-lane units
-    p8_probe_cm2(sh, tid, bpos);
-    p8_probe_single(sh, tid, y, c0, bpos);
-    __syncthreads();
-    P8_T(3);
-    p8_apply_cm2(sh, tid, y, bpos);
-    __syncthreads();
-    P8_T(4);
-    // ---- round 2 of the byte boundary (needs the order-N result and the match model)
-    {
-      const int ismatch = ilog(T, S.match.length);
-      if (tid == 32) sparse_byte(S, ismatch, sh.res2[0]);
-      else if (tid == 64) {
-        // sparseModel1 runs BEFORE wordModel in the reference: it sees the previous byte's word statistics
-        const u32 a = S.spaces, b = S.words, c = S.frstchar, d = S.spafdo;
-        S.spaces = sh.snap_spaces; S.words = sh.snap_words; S.frstchar = sh.snap_frstchar; S.spafdo = sh.snap_spafdo;
-        sparse1_byte(S, ismatch, sh.res2[0]);
-        S.spaces = a; S.words = b; S.frstchar = c; S.spafdo = d;
-      } else if (tid == 96) record_byte(S);
+    // ---- epilogues, ModelStats, the 28 selector sets in the reference's order
+    if (tid == 0) {
+      if (bpos == 7) {
+        for (int k = 0; k < P8_N_CM; ++k) if (!sh.clash[k]) p8_cm(S, k).cn = 0;
+        for (int k = 0; k < P8_N_CM2; ++k) p8_cm2(S, k).index = 0;
+      }
+      xml_stats(S);
+      S.m.nx = sh.unit_off[P8_N_UNITS];
+      smatch_select(S);
+      record_select(S);
+      text_select(S);
+      exe_select(S);
+      main_select(S, sh.res2[0]);
+      Mixer& m = S.m;
+      m.n2 = m.nx;
+      while (m.nx & 7) m.tx[m.nx++] = 0;
     }
-    for (int k = tid; k < P8_SEEN; k += P8_THREADS) sh.u.seen[k] = 0ull;
-    __syncthreads();
-    P8_T(5);
-    if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
-    __syncthreads();
-    P8_T(6);
-    p8_number(sh, tid, y, c0, bpos);
-    __syncthreads();
-    P8_T(7);
-    p8_apply_cm(sh, tid, y, c0, bpos);
-    p8_apply_small(sh, tid, y);
-    __syncthreads();
-    P8_T(8);
-  } else {
-    // ---- inside a byte: probe / number / apply, all map families side by side
-    if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
-    else { p8_probe_cm2(sh, tid, bpos); p8_probe_single(sh, tid, y, c0, bpos); }
-    __syncthreads();
-    P8_T(3);
-    p8_number(sh, tid, y, c0, bpos);
-    __syncthreads();
-    P8_T(7);
-    if (warp < 7) p8_apply_cm(sh, tid, y, c0, bpos);
-    else { p8_apply_cm2(sh, tid, y, bpos); p8_apply_small(sh, tid, y); }
-    __syncthreads();
-    P8_T(8);
   }
-  // ---- epilogues, ModelStats, the 28 selector sets in the reference's order
-  if (tid == 0) {
-    if (bpos == 7) {
-      for (int k = 0; k < P8_N_CM; ++k) if (!sh.clash[k]) p8_cm(S, k).cn = 0;
-      for (int k = 0; k < P8_N_CM2; ++k) p8_cm2(S, k).index = 0;
-    }
-    xml_stats(S);
-    S.m.nx = sh.unit_off[P8_N_UNITS];
-    smatch_select(S);
-    record_select(S);
-    text_select(S);
-    exe_select(S);
-    main_select(S, sh.res2[0]);
-    Mixer& m = S.m;
-    m.n2 = m.nx;
-    while (m.nx & 7) m.tx[m.nx++] = 0;
-  }
-  __syncthreads();
+  __syncthreads();     // the SGD warps join
   P8_T(9);
   // ---- final-mixer SGD (32 weights); the 28 dot products over the cached sets (a selector that moved: write back, load)
   {
@@ -620,7 +646,7 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
       const int err = ((y << 12) - m.pr2) * 7;
       if (err && lane < m.nx2) m.w2[lane] = train_one(m.tx2[lane], m.w2[lane], err);
     }
-    if (warp == 0 && lane < m.ncxt) {        // two selectors on one weight set would need the reference's sequential SGD
+    if (warp == P8_WARPS - 2 && lane < m.ncxt) {        // two selectors on one weight set would need the reference's sequential SGD
       bool dup = false;
       for (int j = 0; j < lane; ++j) dup = dup || m.cxt[j] == m.cxt[lane];
       if (dup) S.error |= ERR_MIXER_ALIAS;

@@ -129,7 +129,9 @@ P8_HD inline int clip8(int v) { return imin(0xFF, imax(0, v)); }
 P8_HD inline void mset(Mixer& m, int cx, int range) { m.cxt[m.ncxt++] = m.base + cx; m.base += range; }
 
 // ---------------------------------------------------------------- match model (:3520-3693)
-P8_HD inline void match_bit(State& S, Out& o) {
+// match_core: bookkeeping, contexts and the two length inputs; match_unit j = 0..8: the three StateMaps, the three stationary
+// maps and the three StationaryMaps behind them (independent of each other: a lane each on the device)
+P8_HD inline void match_core(State& S, Out& o) {
   const Tables& T = *S.T;
   MatchM& M = S.match;
   const int y = S.y, bpos = S.bpos, c0 = S.c0;
@@ -187,22 +189,35 @@ P8_HD inline void match_bit(State& S, Out& o) {
     add(o, sign * (ilog(T, M.length) << 2));
   } else { add(o, 0); add(o, 0); }
   if (M.delta) M.ctx[2] = ((u32)M.expected << 8) | (u32)c0;
-  for (int i = 0; i < 3; ++i) {
-    const u32 c = M.ctx[i];
-    const int p = sm32_p(T, M.sm[i], y, (int)c);
-    if (c != 0) add(o, (stretch(T, p) + 1) >> 1); else add(o, 0);
-  }
-  scm_mix(M.scm[0], o, y);
-  scm_mix(M.scm[1], o, y, 6);
-  scm_mix(M.scm[2], o, y, 5);
-  stm_mix(M.maps[0], o, y, 1, 4, 255);
-  stm_mix(M.maps[1], o, y);
-  stm_mix(M.maps[2], o, y);
   S.st_match_length = M.length;
+}
+P8_HD inline void match_unit(State& S, Out& o, int j) {   // o: at the model's first input
+  const Tables& T = *S.T;
+  MatchM& M = S.match;
+  const int y = S.y;
+  if (j < 3) {
+    o.n += 2 + j;
+    const u32 c = M.ctx[j];
+    const int p = sm32_p(T, M.sm[j], y, (int)c);
+    if (c != 0) add(o, (stretch(T, p) + 1) >> 1); else add(o, 0);
+  } else if (j < 6) {
+    o.n += 5 + 2 * (j - 3);
+    scm_mix(M.scm[j - 3], o, y, 10 - j);
+  } else {
+    o.n += 11 + 2 * (j - 6);
+    stm_mix(M.maps[j - 6], o, y, 1, 4, j == 6 ? 255 : 1023);
+  }
+}
+P8_HD inline void match_bit(State& S, Out& o) {
+  const Out b = o;
+  match_core(S, o);
+  for (int j = 0; j < 9; ++j) { Out u = b; match_unit(S, u, j); }
+  o.n = b.n + 17;
 }
 
 // ---------------------------------------------------------------- sparse match model (:3694-3843)
-P8_HD inline void smatch_core(State& S, Out& o) {
+// smatch_head: bookkeeping and the three length inputs (or eleven zeros); smatch_unit j = 0..3: the StationaryMaps
+P8_HD inline void smatch_head(State& S, Out& o) {
   SparseMatchM& M = S.smatch;
   const u32 offset_[4] = {0, 1, 0, 0}, stride_[4] = {1, 1, 2, 1}, minlen_[4] = {5, 4, 4, 5}, bitmask_[4] = {0xDF, 0xFF, 0xDF, 0x0F};
   const int y = S.y, bpos = S.bpos, c0 = S.c0;
@@ -264,8 +279,18 @@ P8_HD inline void smatch_core(State& S, Out& o) {
       add(o, sign * (1 << imin((int)M.length - 2, 3)) * imin((int)M.length - 1, 8) << 4);
       add(o, sign * 512);
     } else { add(o, 0); add(o, 0); add(o, 0); }
-    for (int i = 0; i < 4; ++i) stm_mix(M.maps[i], o, y, 1, 2);
   } else for (int i = 0; i < 11; ++i) add(o, 0);
+}
+P8_HD inline void smatch_unit(State& S, Out& o, int j) {   // o: at the model's first input
+  if (!S.smatch.valid) return;
+  o.n += 3 + 2 * j;
+  stm_mix(S.smatch.maps[j], o, S.y, 1, 2);
+}
+P8_HD inline void smatch_core(State& S, Out& o) {
+  const Out b = o;
+  smatch_head(S, o);
+  for (int j = 0; j < 4; ++j) { Out u = b; smatch_unit(S, u, j); }
+  o.n = b.n + 11;
 }
 P8_HD inline void smatch_select(State& S) {   // the model's two mixer selector sets (:3839-3840)
   const SparseMatchM& M = S.smatch;
@@ -362,7 +387,7 @@ P8_HD inline void distance_byte(State& S) {   // :4598-4611
   cm_set(M.cm, hash(++i, sx(imin(S.pos - M.pos20, 255) | c << 8)));
   cm_set(M.cm, hash(++i, sx(imin(S.pos - M.posnl, 255) | c << 8)));
 }
-P8_HD inline void pic_bit(State& S, Out& o) {   // :3844-3864
+P8_HD inline void pic_core(State& S) {   // :3844-3858: bit-history updates and the three contexts
   const Tables& T = *S.T;
   PicM& M = S.pic;
   const int y = S.y, bpos = S.bpos;
@@ -374,11 +399,19 @@ P8_HD inline void pic_bit(State& S, Out& o) {   // :3844-3864
   M.cxt[0] = (int)((M.r0 & 0x7) | ((M.r1 >> 4) & 0x38) | ((M.r2 >> 3) & 0xc0));
   M.cxt[1] = (int)(0x100 + ((M.r0 & 1) | ((M.r1 >> 4) & 0x3e) | ((M.r2 >> 2) & 0x40) | ((M.r3 >> 1) & 0x80)));
   M.cxt[2] = (int)(0x200 + ((M.r0 & 0x3f) ^ (M.r1 & 0x3ffe) ^ ((M.r2 << 2) & 0x7f00) ^ ((M.r3 << 5) & 0xf800)));
-  for (int i = 0; i < 3; ++i) {
-    Sm16 s; s.t = M.sm_t + i * 256; s.cxt = M.sm_cxt[i];
-    add(o, stretch(T, sm16_p(s, y, M.t[M.cxt[i]])));
-    M.sm_cxt[i] = s.cxt;
-  }
+}
+P8_HD inline void pic_unit(State& S, Out& o, int i) {   // :3859-3863, o: at the model's first input
+  const Tables& T = *S.T;
+  PicM& M = S.pic;
+  o.n += i;
+  Sm16 s; s.t = M.sm_t + i * 256; s.cxt = M.sm_cxt[i];
+  add(o, stretch(T, sm16_p(s, S.y, M.t[M.cxt[i]])));
+  M.sm_cxt[i] = s.cxt;
+}
+P8_HD inline void pic_bit(State& S, Out& o) {
+  pic_core(S);
+  for (int i = 0; i < 3; ++i) { Out u = o; pic_unit(S, u, i); }
+  o.n += 3;
 }
 
 // ---------------------------------------------------------------- record models (:4204-4474)
