@@ -33,7 +33,7 @@ enum { P8_SEEN = 4096 };
 
 // -DP8_PROF: lane 0 accumulates the cycles between phase boundaries (byte-boundary bits and the others apart)
 #ifdef P8_PROF
-__device__ unsigned long long g_p8_prof[2][64];
+__device__ unsigned long long g_p8_prof[2][96];
 #define P8_T(k) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_p8_prof[sh.prof_row][k], (unsigned long long)(now_ - sh.prof_t)); sh.prof_t = now_; } } while (0)
 #define P8_M0 const long long m0_ = clock64()
 #define P8_M(slot) atomicAdd(&g_p8_prof[sh.prof_row][slot], (unsigned long long)(clock64() - m0_))
@@ -67,6 +67,8 @@ struct P8Shared {
   u32 flag_mask[8];            // ballot of "this context draws" per warp of map lanes
   int flag_base[P8_N_CM];      // index of a map's first draw in draws[]
   u32 draws[P8_CM_LANES + 6];
+  u32 rnd_prev[64]; int rnd_prev_i;   // the generator as the bit found it: flagged contexts compute their own draw from it
+  int any_clash;
   union {
     unsigned long long seen[P8_SEEN];   // open-addressing set of (map, bucket) pairs touched this bit
     struct { double ch[3][32 * 33]; double pb[3][32]; } ols;   // Cholesky factor rows (padded) and a product buffer; byte boundaries only
@@ -120,7 +122,7 @@ static_assert(sizeof(p8::State) % 4 == 0, "state block is copied word by word");
 //  * Cholesky: lane r keeps row r in registers; column c takes row c's finished entries from shared memory;
 //  * forward substitution column by column (row i subtracts w[0..i-1] in ascending order), backward substitution row by
 //    row with the products gathered in shared memory and summed in ascending order.
-__device__ void p8_ols_byte_warp(P8Shared& sh, int k, int lane) {
+__device__ __noinline__ void p8_ols_byte_warp(P8Shared& sh, int k, int lane) {
   using namespace p8;
   State& S = sh.S;
   LinearM& M = S.linear;
@@ -128,57 +130,56 @@ __device__ void p8_ols_byte_warp(P8Shared& sh, int k, int lane) {
   double* blk = M.ols + (size_t)k * OLS_STRIDE;
   double* x = blk; double* w = blk + 32; double* b = blk + 64; double* cov = blk + 96;
   double* chs = sh.u.ols.ch[k]; double* pb = sh.u.ols.pb[k];
+  double* row = chs + lane * 33;
   const unsigned full = 0xffffffffu;
   const double val = (double)(u8)buf(S, 1);
   const double xl = x[lane];
-  double c[32];
+  int km = M.ols_km[k] + 1;
+  const bool solve = km >= 4;
+  {
+    double c[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) c[j] = cov[j * 32 + lane];
-  double bl = b[lane];
+    for (int j = 0; j < 32; ++j) c[j] = cov[j * 32 + lane];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const double xj = __shfl_sync(full, xl, j);
-    c[j] = P8_DADD(P8_DMUL(lambda, c[j]), P8_DMUL(one_minus, P8_DMUL(xj, xl)));
-    cov[j * 32 + lane] = c[j];
+    for (int j = 0; j < 32; ++j) {
+      const double xj = __shfl_sync(full, xl, j);
+      const double v = P8_DADD(P8_DMUL(lambda, c[j]), P8_DMUL(one_minus, P8_DMUL(xj, xl)));
+      cov[j * 32 + lane] = v;
+      if (solve) row[j] = (j == lane) ? P8_DADD(v, nu) : v;     // the matrix is exactly symmetric: column `lane` is row `lane`
+    }
   }
+  double bl = b[lane];
   bl = P8_DADD(P8_DMUL(lambda, bl), P8_DMUL(one_minus, P8_DMUL(xl, val)));
   b[lane] = bl;
-  int km = M.ols_km[k] + 1;
   double wl = w[lane];
-  if (km >= 4) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) if (j == lane) c[j] = P8_DADD(c[j], nu);
+  if (solve) {
+    __syncwarp();
     bool fail = false;
-#pragma unroll
-    for (int col = 0; col < 32; ++col) {
-      if (!fail) {
-        double s = c[col];
-#pragma unroll
-        for (int q = 0; q < col; ++q) s = P8_DSUB(s, P8_DMUL(c[q], chs[col * 33 + q]));
-        const double d = __shfl_sync(full, s, col);
-        if (d > 1E-8) {
-          const double dd = P8_DSQRT(d);
-          c[col] = (lane == col) ? dd : P8_DDIV(s, dd);   // lanes above the diagonal hold values nobody reads
-          chs[lane * 33 + col] = c[col];
-        } else fail = true;
-        __syncwarp();
-      }
+    for (int col = 0; col < 32 && !fail; ++col) {
+      const double* rc = chs + col * 33;
+      double s = row[col];
+#pragma unroll 4
+      for (int q = 0; q < col; ++q) s = P8_DSUB(s, P8_DMUL(row[q], rc[q]));
+      const double d = __shfl_sync(full, s, col);
+      if (d > 1E-8) {
+        const double dd = P8_DSQRT(d);
+        if (lane >= col) row[col] = (lane == col) ? dd : P8_DDIV(s, dd);
+      } else fail = true;
+      __syncwarp();
     }
     if (!fail) {
       double sum = bl;
-#pragma unroll
       for (int q = 0; q < 32; ++q) {
         const double wq = P8_DDIV(__shfl_sync(full, sum, q), chs[q * 33 + q]);
         if (lane == q) wl = wq;
-        sum = P8_DSUB(sum, P8_DMUL(c[q], wq));
+        sum = P8_DSUB(sum, P8_DMUL(row[q], wq));          // rows below q; the others hold values nobody reads
       }
       const double zl = wl;
-#pragma unroll
       for (int i = 31; i >= 0; --i) {
-        pb[lane] = P8_DMUL(c[i], wl);
+        pb[lane] = P8_DMUL(row[i], wl);                   // ch[lane][i] * w[lane], read for lane > i only
         __syncwarp();
         double s = __shfl_sync(full, zl, i);
-#pragma unroll
+#pragma unroll 4
         for (int j = i + 1; j < 32; ++j) s = P8_DSUB(s, pb[j]);
         const double wi = P8_DDIV(s, chs[i * 33 + i]);
         if (lane == i) wl = wi;
@@ -252,7 +253,7 @@ __device__ __forceinline__ int p8_flags_in(const u32* mask, int lo, int hi) {
 
 // ---- the pieces of a bit ----------------------------------------------------------------------------------------------
 // probe of the history maps (lanes P8_CM2_TID0 ..): buckets each context touches this bit
-__device__ __forceinline__ void p8_probe_cm2(P8Shared& sh, int tid, int bpos) {
+__device__ __noinline__ void p8_probe_cm2(P8Shared& sh, int tid, int bpos) {
   int k, i;
   if (!p8_cm2_lane(tid - P8_CM2_TID0, k, i)) return;
   p8::Cm2& m = p8_cm2(sh.S, k);
@@ -261,7 +262,7 @@ __device__ __forceinline__ void p8_probe_cm2(P8Shared& sh, int tid, int bpos) {
   if (n && p8_claim(sh.u.seen, P8_N_CM + k, ids, n)) sh.clash2[k] = 1;
 }
 // pass 1 of the 7-slot maps (warps 0-6, whole warps): aged state, draw flag, touched buckets
-__device__ __forceinline__ void p8_probe_cm(P8Shared& sh, int tid, int y, int c0, int bpos) {
+__device__ __noinline__ void p8_probe_cm(P8Shared& sh, int tid, int y, int c0, int bpos) {
   using namespace p8;
   int k, i;
   bool flag = false;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void p8_probe_cm(P8Shared& sh, int tid, int y, int c0
     if (i < m.cn) {
       ns = cm_next_state(*sh.S.T, m, i, y);
       const int n = cm_touched(m, i, c0, bpos, sh.ids[tid]);
-      if (p8_claim(sh.u.seen, k, sh.ids[tid], n)) sh.clash[k] = 1;
+      if (p8_claim(sh.u.seen, k, sh.ids[tid], n)) { sh.clash[k] = 1; sh.any_clash = 1; }
     }
     sh.ns[tid] = (short)ns;
     flag = ns >= 204;
@@ -280,13 +281,13 @@ __device__ __forceinline__ void p8_probe_cm(P8Shared& sh, int tid, int y, int c0
   if ((tid & 31) == 0) sh.flag_mask[tid >> 5] = mask;
 }
 // the units that are one lane each (warps 8-11)
-__device__ __forceinline__ void p8_probe_single(P8Shared& sh, int tid, int y, int c0, int bpos) {
+__device__ __noinline__ void p8_probe_single(P8Shared& sh, int tid, int y, int c0, int bpos) {
   using namespace p8;
   State& S = sh.S;
   const p8::Tables& T = *S.T;
   if (tid == P8_TID_PIC) pic_core(S);
   else if (tid == P8_TID_MATCH) { Out o = p8_out(sh, sh.unit_off[7]); match_core(S, o); }
-  else if (tid == P8_TID_MATCH + 1) { if (bpos != 0) record_pre(S); }   // on a byte boundary it follows record_byte (p8_number)
+  else if (tid == P8_TID_MATCH + 1) { if (bpos != 0) record_pre(S); }   // on a byte boundary it follows record_byte (round 2)
   else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 10) sh.dmc_st[tid - P8_TID_W10] = dmc_st(T, S.dmc[tid - P8_TID_W10], y);
   else if (tid >= P8_TID_W10 + 10 && tid < P8_TID_W10 + 13) {
     const int r = tid - (P8_TID_W10 + 10);
@@ -300,51 +301,50 @@ __device__ __forceinline__ void p8_probe_single(P8Shared& sh, int tid, int y, in
     add(o, (stretch(T, sm32_p(T, r == 0 ? S.sm0 : S.sm1, y, r == 0 ? c0 : (c0 | (buf(S, 1) << 8)))) + 1) >> 1);
   } else if (tid == P8_TID_W11 + 3) { Out o = p8_out(sh, sh.unit_off[0]); add(o, 64); }
 }
-// between the passes: the record model's per-bit contexts on a byte boundary, the draws
-__device__ __forceinline__ void p8_number(P8Shared& sh, int tid, int y, int c0, int bpos) {
+// x[i0 + 1 + r] of the lagged generator x[i] = x[i-24] ^ x[i-55] from the table as it stood at i0
+__device__ __forceinline__ u32 p8_draw_at(const u32* prev, int i0, int r) {
+  if (r < 24) { const int idx = i0 + 1 + r; return prev[(idx - 24) & 63] ^ prev[(idx - 55) & 63]; }
+  u32 t[64], v = 0;
+  for (int j = 0; j < 64; ++j) t[j] = prev[j];
+  for (int j = 0; j <= r; ++j) { const int idx = i0 + 1 + j; v = t[(idx - 24) & 63] ^ t[(idx - 55) & 63]; t[idx & 63] = v; }
+  return v;
+}
+// advance the generator by the number of flagged contexts (one warp; 24 new values depend on old ones only)
+__device__ __forceinline__ void p8_advance_rnd(P8Shared& sh, int lane) {
+  p8::Rnd& r = sh.S.rnd;
+  const int total = p8_flags_in(sh.flag_mask, 0, P8_CM_LANES);
+  const int i0 = r.i;
+  for (int s0 = 0; s0 < total; s0 += 24) {
+    const int n = min(24, total - s0);
+    const int idx = i0 + 1 + s0 + lane;
+    u32 v = 0;
+    if (lane < n) v = r.table[(idx - 24) & 63] ^ r.table[(idx - 55) & 63];
+    __syncwarp();
+    if (lane < n) r.table[idx & 63] = v;
+    __syncwarp();
+  }
+  if (lane == 0) r.i = i0 + total;
+}
+// A bit in which two contexts of one 7-slot map meet in a bucket: one lane walks the maps in order, running the clashing ones
+// on the spot and laying out the draws of the others (draws[flag_base[k] + rank in map]).
+__device__ __noinline__ void p8_number(P8Shared& sh, int tid, int y, int c0, int bpos) {
   using namespace p8;
   State& S = sh.S;
-  if (tid == P8_TID_W11) { if (bpos == 0) record_pre(S); }
-  else if (tid < 32) {
-    const unsigned full = 0xffffffffu;
-    const int lane = tid;
-    const int cnt = lane < P8_N_CM ? p8_flags_in(sh.flag_mask, c_p8_cm_base[lane], c_p8_cm_base[lane + 1]) : 0;
-    const bool clash = lane < P8_N_CM && sh.clash[lane] != 0;
-    if (!__any_sync(full, clash)) {
-      int incl = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(full, incl, d); if (lane >= d) incl += v; }
-      const int total = __shfl_sync(full, incl, 31);
-      if (lane < P8_N_CM) sh.flag_base[lane] = incl - cnt;
-      Rnd& r = S.rnd;
-      const int i0 = r.i;
-      for (int s0 = 0; s0 < total; s0 += 24) {          // x[i] = x[i-24] ^ x[i-55]: 24 new values depend on old ones only
-        const int n = min(24, total - s0);
-        const int idx = i0 + 1 + s0 + lane;
-        u32 v = 0;
-        if (lane < n) v = r.table[(idx - 24) & 63] ^ r.table[(idx - 55) & 63];
-        __syncwarp();
-        if (lane < n) { r.table[idx & 63] = v; sh.draws[s0 + lane] = v; }
-        __syncwarp();
-      }
-      if (lane == 0) r.i = i0 + total;
-    } else if (lane == 0) {       // a map with two contexts in one bucket: walk the maps in order
-      const int c1 = buf(S, 1);
-      int cur = 0;
-      for (int k = 0; k < P8_N_CM; ++k) {
-        Cm& m = p8_cm(S, k);
-        if (sh.clash[k]) { Out o = p8_out(sh, sh.unit_off[c_p8_cm_unit[k]]); cm_mix(m, o, S.rnd, y, c0, bpos, c1); }
-        else {
-          const int n = p8_flags_in(sh.flag_mask, c_p8_cm_base[k], c_p8_cm_base[k + 1]);
-          sh.flag_base[k] = cur;
-          for (int j = 0; j < n; ++j) sh.draws[cur++] = rnd_next(S.rnd);
-        }
-      }
+  if (tid != 0) return;
+  const int c1 = buf(S, 1);
+  int cur = 0;
+  for (int k = 0; k < P8_N_CM; ++k) {
+    Cm& m = p8_cm(S, k);
+    if (sh.clash[k]) { Out o = p8_out(sh, sh.unit_off[c_p8_cm_unit[k]]); cm_mix(m, o, S.rnd, y, c0, bpos, c1); }
+    else {
+      const int n = p8_flags_in(sh.flag_mask, c_p8_cm_base[k], c_p8_cm_base[k + 1]);
+      sh.flag_base[k] = cur;
+      for (int j = 0; j < n; ++j) sh.draws[cur++] = rnd_next(S.rnd);
     }
   }
 }
 // pass 2
-__device__ __forceinline__ void p8_apply_cm2(P8Shared& sh, int tid, int y, int bpos) {
+__device__ __noinline__ void p8_apply_cm2(P8Shared& sh, int tid, int y, int bpos) {
   int k, i;
   if (!p8_cm2_lane(tid - P8_CM2_TID0, k, i)) return;
   p8::Cm2& m = p8_cm2(sh.S, k);
@@ -356,26 +356,36 @@ __device__ __forceinline__ void p8_apply_cm2(P8Shared& sh, int tid, int y, int b
     sh.res2[k] = p8::cm2_mix_body(m, o, y, bpos);
   }
 }
-__device__ __forceinline__ void p8_apply_cm(P8Shared& sh, int tid, int y, int c0, int bpos) {
+__device__ __noinline__ void p8_apply_cm(P8Shared& sh, int tid, int y, int c0, int bpos) {
   using namespace p8;
+  const bool slow = sh.any_clash != 0;
+  if (!slow && tid < 32) p8_advance_rnd(sh, tid);      // flagged lanes read the snapshot, not the live table
   int k, i;
   if (!p8_cm_lane(tid, k, i)) return;
   Cm& m = p8_cm(sh.S, k);
   if (sh.clash[k] || i >= m.cn) return;
   int ns = sh.ns[tid];
   if (ns >= 204) {
-    const u32 r = sh.draws[sh.flag_base[k] + p8_flags_in(sh.flag_mask, c_p8_cm_base[k], tid)];
+    const u32 r = slow ? sh.draws[sh.flag_base[k] + p8_flags_in(sh.flag_mask, c_p8_cm_base[k], tid)]
+                       : p8_draw_at(sh.rnd_prev, sh.rnd_prev_i, p8_flags_in(sh.flag_mask, 0, tid));
     if (cm_draw_hits(r, ns)) ns -= 4;
   }
   Out o = p8_out(sh, sh.unit_off[c_p8_cm_unit[k]] + 5 * i);
   cm_step(m, i, o, ns, y, c0, bpos, buf(sh.S, 1));
 }
-__device__ __forceinline__ void p8_apply_small(P8Shared& sh, int tid, int y, int bpos) {
+__device__ __noinline__ void p8_apply_small(P8Shared& sh, int tid, int y, int bpos) {
   using namespace p8;
   State& S = sh.S;
   if (tid >= P8_TID_MATCH && tid < P8_TID_MATCH + 9) {   // the nine maps behind the match model
     Out o = p8_out(sh, sh.unit_off[7]);
     match_unit(S, o, tid - P8_TID_MATCH);
+  } else if (tid == P8_TID_MATCH + 9) {                    // ModelStats and the 19 selector sets that do not wait for the order-N map
+    xml_stats(S);
+    S.m.nx = sh.unit_off[P8_N_UNITS];
+    smatch_select(S);
+    record_select(S);
+    text_select(S);
+    exe_select(S);
   } else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 12) {   // the record model's 12 direct maps (contexts selected by record_pre)
     Out o = p8_out(sh, sh.unit_off[24 + (tid - P8_TID_W10)]);
     record_small(S, o, tid - P8_TID_W10);
@@ -500,7 +510,7 @@ __device__ __forceinline__ void p8_sgd(P8Shared& sh, int t) {
 }
 
 // One bit: PAQ8::Perceive(y). All P8_THREADS lanes call it: warps 0-11 evaluate the models, warps 12-15 train the mixer beside them.
-__device__ void p8_bit(P8Shared& sh, int y, int tid) {
+__device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit position after this bit, (S.bpos + 1) & 7
   using namespace p8;
   State& S = sh.S;
   const p8::Tables& T = *S.T;
@@ -517,8 +527,25 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
   }
   if (tid >= 32 && tid < 32 + P8_N_CM) sh.clash[tid - 32] = 0;
   if (tid >= 64 && tid < 64 + P8_N_CM2) { sh.clash2[tid - 64] = 0; sh.res2[tid - 64] = 0; }
+  if (tid == 67) { sh.any_clash = 0; sh.rnd_prev_i = S.rnd.i; }
+  if (tid >= 320 && tid < 384) sh.rnd_prev[tid - 320] = S.rnd.table[tid - 320];
   if (tid >= 96 && tid < 96 + N_SETS) sh.sgd_err[tid - 96] = ((y << 12) - S.m.pr[tid - 96]) * 7;
   if (tid >= 128 && tid < 128 + N_IN / 8) reinterpret_cast<uint4*>(sh.tx_old)[tid - 128] = reinterpret_cast<const uint4*>(S.m.tx)[tid - 128];
+  if (tid >= P8_CM2_TID0 && tid < P8_CM2_TID0 + P8_N_CM2) cm2_begin(p8_cm2(S, tid - P8_CM2_TID0), y, nb);
+  if (warp == P8_WARPS - 1 && nb <= 1) {      // mixer-input offsets of the units (they change on the first two bits of a byte only)
+    const unsigned full = 0xffffffffu;
+    const int a = p8_unit_count(S, lane, nb == 0);
+    const int b = lane + 32 < P8_N_UNITS ? p8_unit_count(S, lane + 32, nb == 0) : 0;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int va = __shfl_up_sync(full, ia, d), vb = __shfl_up_sync(full, ib, d);
+      if (lane >= d) { ia += va; ib += vb; }
+    }
+    const int ta = __shfl_sync(full, ia, 31);
+    sh.unit_off[lane] = ia - a;
+    if (lane + 32 <= P8_N_UNITS) sh.unit_off[lane + 32] = ta + ib - b;
+  }
   for (int k = tid; k < P8_SEEN; k += P8_THREADS) sh.u.seen[k] = 0ull;
   __syncthreads();
   P8_T(0);
@@ -526,36 +553,25 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
   const bool byte_start = bpos == 0;
   if (tid >= P8_MAP_THREADS) p8_sgd(sh, tid - P8_MAP_THREADS);
   else {
-    // ---- mixer-input offsets of the units, history-map prologues
     if (tid == 0) { S.m.nx = S.m.base = S.m.ncxt = 0; }
-    if (warp == P8_MAP_WARPS - 1) {           // two units per lane, prefix over the warp
-      const unsigned full = 0xffffffffu;
-      const int a = p8_unit_count(S, lane, byte_start);
-      const int b = lane + 32 < P8_N_UNITS ? p8_unit_count(S, lane + 32, byte_start) : 0;
-      int ia = a, ib = b;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int va = __shfl_up_sync(full, ia, d), vb = __shfl_up_sync(full, ib, d);
-        if (lane >= d) { ia += va; ib += vb; }
-      }
-      const int ta = __shfl_sync(full, ia, 31);
-      sh.unit_off[lane] = ia - a;
-      if (lane + 32 <= P8_N_UNITS) sh.unit_off[lane + 32] = ta + ib - b;
-    }
-    if (tid >= P8_CM2_TID0 && tid < P8_CM2_TID0 + P8_N_CM2) cm2_begin(p8_cm2(S, tid - P8_CM2_TID0), y, bpos);
     if (byte_start) {
       // ---- byte boundary, round 1: context computation, one model per lane / warp
       {
         P8_M0;
         if (warp < 3) p8_ols_byte_warp(sh, warp, lane);
-        else if (lane == 0) {
+        else if (warp == 8) {       // the text model: state on one lane, its 33 contexts side by side
+          if (lane == 0) text_update(S);
+          __syncwarp();
+          const int n = text_contexts(S, CtxSel{lane, 32});
+          __syncwarp();
+          if (lane == 0) S.text.map.index = n;
+        } else if (lane == 0) {
           switch (warp) {
             case 3: ordern_byte(S); break;
             case 4: distance_byte(S); record1_byte(S); break;
             case 5: word_byte(S); break;
             case 6: nest_byte(S); indirect_byte(S); break;
             case 7: xml_byte(S); break;
-            case 8: text_update(S); text_contexts(S); break;
             case 9: exe_byte(S); break;
             case 10: {
               const u8 W = (u8)buf(S, 1), WW = (u8)buf(S, 2), WWW = (u8)buf(S, 3);
@@ -588,7 +604,7 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
           S.spaces = sh.snap_spaces; S.words = sh.snap_words; S.frstchar = sh.snap_frstchar; S.spafdo = sh.snap_spafdo;
           sparse1_byte(S, ismatch, sh.res2[0]);
           S.spaces = a; S.words = b; S.frstchar = c; S.spafdo = d;
-        } else if (tid == 96) record_byte(S);
+        } else if (tid == 96) { record_byte(S); record_pre(S); }
       }
       for (int k = tid; k < P8_SEEN; k += P8_MAP_THREADS) sh.u.seen[k] = 0ull;
       p8_sync_maps();
@@ -596,26 +612,32 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
       if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
       p8_sync_maps();
       P8_T(6);
-      p8_number(sh, tid, y, c0, bpos);
-      p8_sync_maps();
+      if (sh.any_clash) { p8_number(sh, tid, y, c0, bpos); p8_sync_maps(); }
       P8_T(7);
       p8_apply_cm(sh, tid, y, c0, bpos);
       p8_apply_small(sh, tid, y, bpos);
       p8_sync_maps();
       P8_T(8);
     } else {
-      p8_sync_maps();
-      P8_T(1);
       // ---- inside a byte: probe / number / apply, all map families side by side
-      if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
-      else { p8_probe_cm2(sh, tid, bpos); p8_probe_single(sh, tid, y, c0, bpos); }
+      {
+        P8_M0;
+        if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
+        else { p8_probe_cm2(sh, tid, bpos); p8_probe_single(sh, tid, y, c0, bpos); }
+        __syncwarp();
+        if (lane == 0) P8_M(24 + warp);
+      }
       p8_sync_maps();
       P8_T(3);
-      p8_number(sh, tid, y, c0, bpos);
-      p8_sync_maps();
+      if (sh.any_clash) { p8_number(sh, tid, y, c0, bpos); p8_sync_maps(); }
       P8_T(7);
-      if (warp < 7) p8_apply_cm(sh, tid, y, c0, bpos);
-      else { p8_apply_cm2(sh, tid, y, bpos); p8_apply_small(sh, tid, y, bpos); }
+      {
+        P8_M0;
+        if (warp < 7) p8_apply_cm(sh, tid, y, c0, bpos);
+        else { p8_apply_cm2(sh, tid, y, bpos); p8_apply_small(sh, tid, y, bpos); }
+        __syncwarp();
+        if (lane == 0) P8_M(48 + warp);
+      }
       p8_sync_maps();
       P8_T(8);
     }
@@ -625,12 +647,6 @@ __device__ void p8_bit(P8Shared& sh, int y, int tid) {
         for (int k = 0; k < P8_N_CM; ++k) if (!sh.clash[k]) p8_cm(S, k).cn = 0;
         for (int k = 0; k < P8_N_CM2; ++k) p8_cm2(S, k).index = 0;
       }
-      xml_stats(S);
-      S.m.nx = sh.unit_off[P8_N_UNITS];
-      smatch_select(S);
-      record_select(S);
-      text_select(S);
-      exe_select(S);
       main_select(S, sh.res2[0]);
       Mixer& m = S.m;
       m.n2 = m.nx;
@@ -743,7 +759,7 @@ __global__ void __launch_bounds__(P8_THREADS, 1) paq8_kernel(const ChunkArgs* __
       for (int k = tid; k < p8::N_OUT; k += P8_THREADS) out[k] = sh.S.codes[k];
     }
     const int y = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
-    p8_bit(sh, y, tid);
+    p8_bit(sh, y, (int)((t + 1) & 7), tid);
   }
   p8_leave(sh, g, gT, tid);
 }
@@ -753,8 +769,9 @@ __global__ void __launch_bounds__(P8_THREADS, 1) paq8_bit_kernel(p8::State* g, i
   extern __shared__ __align__(16) unsigned char p8_raw[];
   P8Shared& sh = *reinterpret_cast<P8Shared*>(p8_raw);
   const int tid = threadIdx.x;
+  const int nb = (g->bpos + 1) & 7;       // read from HBM: the shared copy is being updated by lane 0 inside p8_bit
   const p8::Tables* gT = p8_enter(sh, g, tid);
-  p8_bit(sh, y, tid);
+  p8_bit(sh, y, nb, tid);
   if (ext_bit) for (int k = tid; k < p8::N_OUT; k += P8_THREADS) ext_bit[431 + k] = sh.S.codes[k];
   p8_leave(sh, g, gT, tid);
 }

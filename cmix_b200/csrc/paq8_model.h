@@ -156,6 +156,16 @@ P8_HD inline void sm32_update(const Tables& T, Sm32& s, int y, int limit) {
   p0 += delta & 0xfffffc00u;
   s.t[s.cxt] = p0;
 }
+// StateMap32::p with the loads hoisted: `old` is t[old_cxt] read before any store of this bit, `fresh` is t[cx] read before the
+// update below is stored (both from the same table; when cx == old_cxt the updated value is forwarded). Same result as sm32_p.
+P8_HD inline u32 sm32_updated(const Tables& T, u32 p0, int y, int limit) {
+  const int n = p0 & 1023, pr = (int)(p0 >> 10);
+  if (n < limit) ++p0; else p0 = (p0 & 0xfffffc00u) | (u32)limit;
+  const int target = y << 22;
+  const u32 delta = (u32)((target - pr) >> 3) * (u32)T.dt[n];
+  p0 += delta & 0xfffffc00u;
+  return p0;
+}
 P8_HD inline int sm32_p(const Tables& T, Sm32& s, int y, int cx, int limit = 1023) {
   sm32_update(T, s, y, limit);
   s.cxt = cx;
@@ -305,6 +315,9 @@ P8_HD inline int cm_touched(const Cm& m, int i, int c0, int bp, u32* ids) { retu
 P8_HD inline int cm_step(Cm& m, int i, Out& o, int ns, int y, int c0, int bp, int c1) {
   const Tables& T = *o.T;
   u8* t = m.t;
+  u16* smt = m.sm_t + i * 256;
+  const int so = m.sm_cxt[i];
+  const u16 sm_old = smt[so];              // loaded before the bucket walk: its address is known from the previous bit
   if (m.cp[i] != P8_NULL) t[m.cp[i]] = (u8)ns;
   if (bp > 1 && t[m.runp[i]] == 0) m.cp[i] = P8_NULL;
   else {
@@ -332,9 +345,12 @@ P8_HD inline int cm_step(Cm& m, int i, Out& o, int ns, int y, int c0, int bp, in
     add(o, b * c);
   } else add(o, 0);
   const int s = m.cp[i] != P8_NULL ? t[m.cp[i]] : 0;
-  Sm16 smi; smi.t = m.sm_t + i * 256; smi.cxt = m.sm_cxt[i];
-  const int p1 = sm16_p(smi, y, s);
-  m.sm_cxt[i] = smi.cxt;
+  u16 fresh = smt[s];
+  const u16 upd = (u16)(sm_old + (((y << 16) - (int)sm_old + 128) >> 8));   // StateMap16 update of the previous bit's cell
+  if (s == so) fresh = upd;
+  smt[so] = upd;
+  m.sm_cxt[i] = s;
+  const int p1 = fresh >> 4;
   const int st = (stretch(T, p1) + 2) >> 2;
   add(o, st);
   add(o, (p1 - 2047 + 4) >> 3);
@@ -363,6 +379,15 @@ P8_HD inline void cm2_set(Cm2& m, u64 ctx) {
   m.chk[m.index] = (u16)(checksum64(ctx, m.hashbits, 16) & 0xffff);
   m.index++;
 }
+// context lists shared by a warp: lane `lane` of `lanes` computes the contexts k with k % lanes == lane (lanes == 1: all of them)
+struct CtxSel { int lane, lanes; };
+P8_HD inline bool ctx_mine(const CtxSel& s, int k) { return s.lanes == 1 || (k % s.lanes) == s.lane; }
+P8_HD inline void cm2_put(Cm2& m, int k, u64 ctx) {
+  ctx = hash(ctx, (u64)k);
+  m.cxt[k] = finalize64(ctx, m.hashbits);
+  m.chk[k] = (u16)(checksum64(ctx, m.hashbits, 16) & 0xffff);
+}
+#define P8_CM2_SET(sel, m, k, expr) do { if (ctx_mine(sel, k)) cm2_put(m, k, (expr)); ++k; } while (0)
 // ---- ContextMap2::mix (:1294-1358) including Update (:1204-1260), cut into prologue / per-context step / epilogue
 P8_HD inline void cm2_begin(Cm2& m, int y, int bpos) {
   m.last_bit = (u8)y;
@@ -375,6 +400,10 @@ P8_HD inline int cm2_touched(const Cm2& m, int i, int bp, u32* ids) { return tou
 P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
   const Tables& T = *o.T;
   u8* t = m.t;
+  // the three StateMap cells trained this bit: their addresses are known from the previous bit, so the loads go first
+  u32* c8 = m.m8_t + i * 256; u32* c12 = m.m12_t + i * 4608; u32* c6 = m.m6_t + i * 72;
+  const int o8 = m.m8_cxt[i], o12 = m.m12_cxt[i], o6 = m.m6_cxt[i];
+  const u32 old8 = c8[o8], old12 = c12[o12], old6 = c6[o6];
   if (m.bs[i] != P8_NULL) t[m.bs[i]] = T.state[t[m.bs[i]]][y];
   if (bpos > 1 && t[m.bh[i]] == 0) m.bs[i] = P8_NULL;
   else {
@@ -400,28 +429,36 @@ P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
   }
   int state = m.bs[i] != P8_NULL ? t[m.bs[i]] : 0;
   const int result = state > 0;
-  Sm32 q; q.n = 0;
-  q.t = m.m8_t + i * 256; q.cxt = m.m8_cxt[i];
-  int p1 = sm32_p(T, q, y, state);
-  m.m8_cxt[i] = q.cxt;
+  const u8* h = t + m.bh[i];
+  const u8 h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
   int n0 = T.state[state][2], n1 = T.state[state][3], k = -~n1;
   k = (k * 64) / (k - ~n0);
   n0 = -!n0; n1 = -!n1;
-  const u8* h = t + m.bh[i];
-  if ((u32)((h[1] + 256) >> (8 - bpos)) == m.bits) {
-    const int rs = h[0];
-    const int sign = ((h[1] >> (7 - bpos)) & 1) * 2 - 1;
+  int hist;
+  if (m.has_history[i]) {
+    hist = (h1 >> (7 - bpos)) & 1;
+    hist |= ((h2 >> (7 - bpos)) & 1) * 2;
+    hist |= ((h3 >> (7 - bpos)) & 1) * 4;
+  } else hist = 8;
+  // the cells predicted from: loaded before the trained cells are stored, forwarded when a map stays on its cell
+  const int x8 = state, x12 = (hist << 9) | (bpos << 6) | k, x6 = (hist << 3) | bpos;
+  u32 f8 = c8[x8], f12 = c12[x12], f6 = c6[x6];
+  const u32 u8v = sm32_updated(T, old8, y, 1023), u12v = sm32_updated(T, old12, y, 1023), u6v = sm32_updated(T, old6, y, 1023);
+  if (x8 == o8) f8 = u8v;
+  if (x12 == o12) f12 = u12v;
+  if (x6 == o6) f6 = u6v;
+  c8[o8] = u8v; c12[o12] = u12v; c6[o6] = u6v;
+  m.m8_cxt[i] = x8; m.m12_cxt[i] = x12; m.m6_cxt[i] = x6;
+  int p1 = (int)(f8 >> 20);
+  if ((u32)((h1 + 256) >> (8 - bpos)) == m.bits) {
+    const int rs = h0;
+    const int sign = ((h1 >> (7 - bpos)) & 1) * 2 - 1;
     add(o, sign * (ilog(T, rs + 1) << (3 - (rs & 1))));
-  } else if (bpos > 0 && (h[0] & 1) > 0) {
-    if ((u32)((h[2] + 256) >> (8 - bpos)) == m.bits) add(o, (((h[2] >> (7 - bpos)) & 1) * 2 - 1) * 128);
-    else if (m.has_history[i] && (u32)((h[3] + 256) >> (8 - bpos)) == m.bits) add(o, (((h[3] >> (7 - bpos)) & 1) * 2 - 1) * 128);
+  } else if (bpos > 0 && (h0 & 1) > 0) {
+    if ((u32)((h2 + 256) >> (8 - bpos)) == m.bits) add(o, (((h2 >> (7 - bpos)) & 1) * 2 - 1) * 128);
+    else if (m.has_history[i] && (u32)((h3 + 256) >> (8 - bpos)) == m.bits) add(o, (((h3 >> (7 - bpos)) & 1) * 2 - 1) * 128);
     else add(o, 0);
   } else add(o, 0);
-  if (m.has_history[i]) {
-    state = (h[1] >> (7 - bpos)) & 1;
-    state |= ((h[2] >> (7 - bpos)) & 1) * 2;
-    state |= ((h[3] >> (7 - bpos)) & 1) * 4;
-  } else state = 8;
   const int st = stretch(T, p1) >> 2;
   add(o, st);
   add(o, (p1 - 2047) >> 3);
@@ -429,12 +466,8 @@ P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
   const int p0 = 255 - p1;
   add(o, st * iabs(n1 - n0));
   add(o, (p1 & n0) - (p0 & n1));
-  q.t = m.m12_t + i * 4608; q.cxt = m.m12_cxt[i];
-  add(o, stretch(T, sm32_p(T, q, y, (state << 9) | (bpos << 6) | k)) >> 2);
-  m.m12_cxt[i] = q.cxt;
-  q.t = m.m6_t + i * 72; q.cxt = m.m6_cxt[i];
-  add(o, stretch(T, sm32_p(T, q, y, (state << 3) | bpos)) >> 2);
-  m.m6_cxt[i] = q.cxt;
+  add(o, stretch(T, (int)(f12 >> 20)) >> 2);
+  add(o, stretch(T, (int)(f6 >> 20)) >> 2);
   return result;
 }
 // In-order evaluation. The reference updates ALL contexts before predicting from any (two loops); the per-context fusion

@@ -225,7 +225,9 @@ P8_HD inline void text_update(State& S) {
   S.st_text_mask = (u8)(M.masks[1] & 0xFF);
 }
 
-P8_HD inline void text_contexts(State& S) {
+// The 33 contexts of the text model's history map (:3376-3515). Pure apart from the sets: with sel.lanes > 1 every lane of a warp walks
+// the list and computes only its own contexts (k % lanes == lane); returns the new context count for the caller to store.
+P8_HD inline int text_contexts(State& S, const CtxSel sel) {
   const Tables& T = *S.T;
   TextM& M = S.text;
   Cm2& map = M.map;
@@ -233,57 +235,59 @@ P8_HD inline void text_contexts(State& S) {
   const Word& cw = P8_CW; const Word& pw = P8_PW;
   const u16 w = (u16)(((M.state == TP_ReadingWord) ? cw.hash[1] : pw.hash[1]) & 0xFFFF);
   const u32 h = (u32)(((M.state == TP_ReadingWord) ? cw.hash[1] : pw.hash[2]) * 271 + c);
-  u64 i = (u64)M.state << 6;
+  const u64 i0 = (u64)M.state << 6;
+  int n = map.index;
   const Word& w2 = tw(M, M.lang_pid, 2); const Word& w3 = tw(M, M.lang_pid, 3);
   Sentence& sen = tsen(M, 0); Segment& seg = tseg(M, 0);
   const u32 wl0 = M.word_length[0], wl1 = M.word_length[1], gap = M.word_gap;
-  cm2_set(map, M.parse_ctx);
-  cm2_set(map, hash(i++, cw.hash[0], pw.hash[0], (u64)((M.last_upper < wl0) | ((M.last_digit < wl0 + gap) << 1))));
-  cm2_set(map, hash(i++, cw.hash[1], w2.hash[1], (u64)imin(10, (int)ilog2((u32)M.numbers[0])),
+  P8_CM2_SET(sel, map, n, M.parse_ctx);
+  P8_CM2_SET(sel, map, n, hash((i0 + 0), cw.hash[0], pw.hash[0], (u64)((M.last_upper < wl0) | ((M.last_digit < wl0 + gap) << 1))));
+  P8_CM2_SET(sel, map, n, hash((i0 + 1), cw.hash[1], w2.hash[1], (u64)imin(10, (int)ilog2((u32)M.numbers[0])),
                     (u64)((M.last_upper < M.last_letter + wl1) | ((M.last_letter > 3) << 1) | ((M.last_letter > 0 && wl1 < 3) << 2))));
-  cm2_set(map, hash(i++, cw.hash[1] & 0xFFF, (u64)(M.masks[1] & 0x3FF), w3.hash[2],
+  P8_CM2_SET(sel, map, n, hash((i0 + 2), cw.hash[1] & 0xFFF, (u64)(M.masks[1] & 0x3FF), w3.hash[2],
                     (u64)((M.last_digit < wl0 + gap) | ((M.last_upper < M.last_letter + wl1) << 1) | ((M.spaces & 0x7F) << 2))));
-  cm2_set(map, hash(i++, cw.hash[1], pw.hash[3], w2.hash[3]));
-  cm2_set(map, hash(i++, (u64)(h & 0x7FFF), w2.hash[1] & 0xFFF, w3.hash[1] & 0xFFF));
-  cm2_set(map, hash(i++, cw.hash[1], c, (sen.verb_index < sen.word_count) ? sen.last_verb.hash[1] : 0));
-  cm2_set(map, hash(i++, pw.hash[2], (u64)(M.masks[1] & 0xFC), lc, gap));
-  cm2_set(map, hash(i++, (M.last_letter == 0) ? cw.hash[1] : pw.hash[1], c, seg.first_word.hash[2], (u64)imin(3, (int)ilog2(seg.word_count + 1))));
-  cm2_set(map, hash(i++, cw.hash[1], c, tseg(M, 1).first_word.hash[3]));
-  cm2_set(map, hash(i++, (u64)imax(31, lc), (u64)(M.masks[1] & 0xFFC), (u64)((M.spaces & 0xFE) | (M.last_punct < M.last_letter)),
+  P8_CM2_SET(sel, map, n, hash((i0 + 3), cw.hash[1], pw.hash[3], w2.hash[3]));
+  P8_CM2_SET(sel, map, n, hash((i0 + 4), (u64)(h & 0x7FFF), w2.hash[1] & 0xFFF, w3.hash[1] & 0xFFF));
+  P8_CM2_SET(sel, map, n, hash((i0 + 5), cw.hash[1], c, (sen.verb_index < sen.word_count) ? sen.last_verb.hash[1] : 0));
+  P8_CM2_SET(sel, map, n, hash((i0 + 6), pw.hash[2], (u64)(M.masks[1] & 0xFC), lc, gap));
+  P8_CM2_SET(sel, map, n, hash((i0 + 7), (M.last_letter == 0) ? cw.hash[1] : pw.hash[1], c, seg.first_word.hash[2], (u64)imin(3, (int)ilog2(seg.word_count + 1))));
+  P8_CM2_SET(sel, map, n, hash((i0 + 8), cw.hash[1], c, tseg(M, 1).first_word.hash[3]));
+  P8_CM2_SET(sel, map, n, hash((i0 + 9), (u64)imax(31, lc), (u64)(M.masks[1] & 0xFFC), (u64)((M.spaces & 0xFE) | (M.last_punct < M.last_letter)),
                     (u64)((M.mask_upper & 0xFF) | (((0x100 | M.first_letter) * (wl0 > 1)) << 8))));
-  cm2_set(map, hash(i++, column, (u64)imin(7, (int)ilog2(M.last_upper + 1)), (u64)ilog2(M.last_punct + 1)));
-  cm2_set(map, (u64)(u32)((column & 0xF8) | (M.masks[1] & 3) | ((M.prev_newline - M.last_newline > 63) << 2) | (umin(3, M.last_letter) << 8) | ((u32)M.first_char << 10) |
+  P8_CM2_SET(sel, map, n, hash((i0 + 10), column, (u64)imin(7, (int)ilog2(M.last_upper + 1)), (u64)ilog2(M.last_punct + 1)));
+  P8_CM2_SET(sel, map, n, (u64)(u32)((column & 0xF8) | (M.masks[1] & 3) | ((M.prev_newline - M.last_newline > 63) << 2) | (umin(3, M.last_letter) << 8) | ((u32)M.first_char << 10) |
                           ((M.commas > 4) << 18) | ((m2 >= 1 && m2 <= 5) << 19) | ((m2 >= 6 && m2 <= 10) << 20) | ((m2 == 11 || m2 == 12) << 21) |
                           ((M.last_upper < column) << 22) | ((M.last_digit < column) << 23) | ((column < M.prev_newline - M.last_newline) << 24)));
-  cm2_set(map, hash((u64)((2 * column) / 3), (u64)(umin(13, M.last_punct) + (M.last_punct > 16) + (M.last_punct > 32) + M.mask_punct * 16), (u64)ilog2(M.last_upper + 1),
+  P8_CM2_SET(sel, map, n, hash((u64)((2 * column) / 3), (u64)(umin(13, M.last_punct) + (M.last_punct > 16) + (M.last_punct > 32) + M.mask_punct * 16), (u64)ilog2(M.last_upper + 1),
                     (u64)ilog2(M.prev_newline - M.last_newline), (u64)(((M.masks[1] & 3) == 0) | ((m2 < 6) << 1) | ((m2 < 11) << 2))));
-  cm2_set(map, hash(i++, (u64)(column >> 1), (u64)(M.spaces & 0xF)));
-  cm2_set(map, hash((u64)(M.masks[3] & 0x3F), (u64)imin((imax((int)wl0, 3) - 2) * (wl0 < 8), 3), (u64)(M.first_letter * (wl0 < 5)), (u64)(w & 0x3FF),
+  P8_CM2_SET(sel, map, n, hash((i0 + 11), (u64)(column >> 1), (u64)(M.spaces & 0xF)));
+  P8_CM2_SET(sel, map, n, hash((u64)(M.masks[3] & 0x3F), (u64)imin((imax((int)wl0, 3) - 2) * (wl0 < 8), 3), (u64)(M.first_letter * (wl0 < 5)), (u64)(w & 0x3FF),
                     (u64)((c == buf(S, 2)) | ((M.masks[2] > 0) << 1) | ((M.last_punct < wl0 + gap) << 2) | ((M.last_upper < wl0) << 3) | ((M.last_digit < wl0 + gap) << 4) |
                           ((M.last_punct < 2 + wl0 + gap + wl1) << 5))));
-  cm2_set(map, hash(i++, w, c, M.num_hashes[1]));
-  cm2_set(map, hash(i++, w, c, (u64)(llog(T, (u32)S.pos - M.word_pos[w]) >> 1)));
-  cm2_set(map, hash(i++, w, c, M.topic.hash[1] & 0x7FFF));
-  cm2_set(map, hash(i++, M.num_length[0], c, M.topic.hash[1] & 0x7FFF));
-  cm2_set(map, hash(i++, (u64)((M.last_letter > 0) ? c : 0x100), (u64)(M.masks[1] & 0xFFC), (u64)(M.nest_hash & 0x7FF)));
-  cm2_set(map, hash(i++, (u64)(u32)((u32)w * 17 + c), (u64)(M.masks[3] & 0x1FF),
+  P8_CM2_SET(sel, map, n, hash((i0 + 12), w, c, M.num_hashes[1]));
+  P8_CM2_SET(sel, map, n, hash((i0 + 13), w, c, (u64)(llog(T, (u32)S.pos - M.word_pos[w]) >> 1)));
+  P8_CM2_SET(sel, map, n, hash((i0 + 14), w, c, M.topic.hash[1] & 0x7FFF));
+  P8_CM2_SET(sel, map, n, hash((i0 + 15), M.num_length[0], c, M.topic.hash[1] & 0x7FFF));
+  P8_CM2_SET(sel, map, n, hash((i0 + 16), (u64)((M.last_letter > 0) ? c : 0x100), (u64)(M.masks[1] & 0xFFC), (u64)(M.nest_hash & 0x7FF)));
+  P8_CM2_SET(sel, map, n, hash((i0 + 17), (u64)(u32)((u32)w * 17 + c), (u64)(M.masks[3] & 0x1FF),
                     (u64)(((sen.verb_index == 0 && sen.last_verb.len() > 0) << 6) | ((wl1 > 3) << 5) | ((seg.word_count == 0) << 4) |
                           ((sen.segment_count == 0 && sen.word_count < 2) << 3) | ((M.last_punct >= M.last_letter + wl1 + gap) << 2) |
                           ((M.last_upper < M.last_letter + wl1) << 1) | (M.last_upper < wl0 + gap + wl1))));
-  cm2_set(map, hash(i++, c, pw.hash[2], (u64)(M.first_letter * (wl0 < 6)), (u64)(((M.last_punct < wl0 + gap) << 1) | (M.last_punct >= M.last_letter + wl1 + gap))));
+  P8_CM2_SET(sel, map, n, hash((i0 + 18), c, pw.hash[2], (u64)(M.first_letter * (wl0 < 6)), (u64)(((M.last_punct < wl0 + gap) << 1) | (M.last_punct >= M.last_letter + wl1 + gap))));
   {
     const Word& wx = tw(M, M.lang_pid, 1 + (wl0 == 0));
-    cm2_set(map, hash(i++, (u64)(u32)((u32)w * 23 + c), wx.L[wx.s], (u64)(M.first_letter * (wl0 < 7))));
+    P8_CM2_SET(sel, map, n, hash((i0 + 19), (u64)(u32)((u32)w * 23 + c), wx.L[wx.s], (u64)(M.first_letter * (wl0 < 7))));
   }
-  cm2_set(map, hash(i++, column, (u64)(M.spaces & 7), (u64)(M.nest_hash & 0x7FF)));
-  cm2_set(map, hash(i++, cw.hash[1], (u64)((M.last_upper < column) | ((M.last_upper < wl0) << 1)), (u64)umin(5, wl0)));
-  cm2_set(map, M.masks[4]);
-  cm2_set(map, hash((u64)(u32)M.ascii_mask, (u64)(u32)(M.ascii_mask >> 32)));
-  cm2_set(map, M.ascii_mask & ((1 << 20) - 1));
-  cm2_set(map, M.ascii_mask & ((1 << 10) - 1));
-  cm2_set(map, hash((M.ascii_mask >> 5) & ((1 << 30) - 1), (u64)buf(S, 1)));
-  cm2_set(map, hash((M.ascii_mask >> 10) & ((1 << 30) - 1), (u64)buf(S, 1), (u64)buf(S, 2)));
-  cm2_set(map, hash((M.ascii_mask >> 15) & ((1 << 30) - 1), (u64)buf(S, 1), (u64)buf(S, 2), (u64)buf(S, 3)));
+  P8_CM2_SET(sel, map, n, hash((i0 + 20), column, (u64)(M.spaces & 7), (u64)(M.nest_hash & 0x7FF)));
+  P8_CM2_SET(sel, map, n, hash((i0 + 21), cw.hash[1], (u64)((M.last_upper < column) | ((M.last_upper < wl0) << 1)), (u64)umin(5, wl0)));
+  P8_CM2_SET(sel, map, n, M.masks[4]);
+  P8_CM2_SET(sel, map, n, hash((u64)(u32)M.ascii_mask, (u64)(u32)(M.ascii_mask >> 32)));
+  P8_CM2_SET(sel, map, n, M.ascii_mask & ((1 << 20) - 1));
+  P8_CM2_SET(sel, map, n, M.ascii_mask & ((1 << 10) - 1));
+  P8_CM2_SET(sel, map, n, hash((M.ascii_mask >> 5) & ((1 << 30) - 1), (u64)buf(S, 1)));
+  P8_CM2_SET(sel, map, n, hash((M.ascii_mask >> 10) & ((1 << 30) - 1), (u64)buf(S, 1), (u64)buf(S, 2)));
+  P8_CM2_SET(sel, map, n, hash((M.ascii_mask >> 15) & ((1 << 30) - 1), (u64)buf(S, 1), (u64)buf(S, 2), (u64)buf(S, 3)));
+  return n;
 }
 
 P8_HD inline void text_select(State& S);
@@ -291,7 +295,7 @@ P8_HD inline void text_bit(State& S, Out& o) {
   TextM& M = S.text;
   if (S.bpos == 0) {
     text_update(S);
-    text_contexts(S);
+    M.map.index = text_contexts(S, CtxSel{0, 1});
   }
   cm2_mix(M.map, o, S.y, S.bpos);
   text_select(S);

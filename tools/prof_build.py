@@ -45,7 +45,7 @@ def run(n_bytes):
     P.code_bytes(text[:n_bytes])
     lib = load_library()
     sm_mhz = torch.cuda.get_device_properties(0).clock_rate / 1e3 if hasattr(torch.cuda.get_device_properties(0), "clock_rate") else 1965.0
-    for name, fn, rows in (("paq8", "cmixb200_p8_prof", 64), ("fxcm", "cmixb200_fx_prof", 24)):
+    for name, fn, rows in (("paq8", "cmixb200_p8_prof", 96), ("fxcm", "cmixb200_fx_prof", 24)):
         if not hasattr(lib, fn):
             continue
         buf = (ctypes.c_ulonglong * (2 * rows))()
@@ -55,7 +55,7 @@ def run(n_bytes):
     for w, k in enumerate(["mix", "small", "lstm", "ppmd", "fxcm", "paq8"]):
         ms, n = P.kernel_ms(w)
         print("%-6s %8.2f us/bit (%d launches)" % (k, ms * 1e3 / (n_bytes * 8), n))
-    for name, fn, rows in (("paq8", "cmixb200_p8_prof", 64), ("fxcm", "cmixb200_fx_prof", 24)):
+    for name, fn, rows in (("paq8", "cmixb200_p8_prof", 96), ("fxcm", "cmixb200_fx_prof", 24)):
         try:
             f = getattr(lib, fn)
         except AttributeError:
