@@ -31,6 +31,8 @@ import time
 import numpy as np
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context: one work queue per library stream
+os.environ.setdefault("CMIXB200_PPMD_MB", "1024")            # PPMD arenas: the library's default is the reference's 14 000 MB heap per stream;
+                                                             # the bench files are 20 KB, 1 GB is ample and lets the aggregate figure fit more streams
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -83,6 +85,13 @@ def bench_text(n_bytes, stream_id=0):
     return np.frombuffer(synth_text(n_bytes, SEED + stream_id), dtype=np.uint8).copy()
 
 
+def bench_stream(n_file, stream_id=0):
+    """What the predictor sees for an n_file-byte input under `cmix -n`: runner.cpp's stream, i.e. NoPreprocess's 5-byte block
+    header (type DEFAULT, big-endian length; preprocessor.cpp:591-600, one segment) followed by the file."""
+    head = np.frombuffer(bytes([0]) + int(n_file).to_bytes(4, "big"), dtype=np.uint8)
+    return np.concatenate([head, bench_text(n_file, stream_id)])
+
+
 N_E2E = 10
 N_AGG = 3
 
@@ -90,7 +99,7 @@ N_AGG = 3
 def file_bytes(B, W, K):
     """Length of the synthetic file of one stream: every step of the run consumes fresh bytes of it. The vocabulary (the LSTM's
     symbol set, runner.cpp:196-203) is taken over the whole file, in both arms."""
-    return B * (W + K + 1 + N_E2E + N_AGG)
+    return B * (W + K + 1 + N_E2E + N_AGG) - 5      # + the 5-byte block header = a whole number of steps
 
 
 def reference_run(binary, n_file, n_bytes, step_bytes):
@@ -120,7 +129,7 @@ def cpu_baseline(n_file, sample_bytes):
     r = r_fast or r_strict
     return {"value": r["bytes"] / r["code_s"] / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
             "build": "-Ofast -march=x86-64-v3 (project flags)" if r_fast else "-O2 strict FP",
-            "sample": "first %d bytes of the same file as stream 0 (same vocabulary), whole predictor, one stream, taskset -c 0, constructor (%.1f s) excluded" % (r["bytes"], r["ctor_s"]),
+            "sample": "first %d bytes of the same stream as stream 0 (block header + file, same vocabulary), whole predictor, one stream, taskset -c 0, constructor (%.1f s) excluded" % (r["bytes"], r["ctor_s"]),
             "strict_value": r_strict["bytes"] / r_strict["code_s"] / 1e6, "bpc_reference": r_strict["bpc"], "bpc_reference_fast_build": r_fast["bpc"] if r_fast else None}
 
 
@@ -141,7 +150,7 @@ def main():
     S, B, K, W = args.streams, args.step_bytes, args.steps, args.warmup
     config = {"workload": "configs[1]: synthetic enwik8-shaped ASCII text (seed 0xE9E80001), `cmix -n` equivalent; complete predictor, every model "
                           "group device resident (small models, PPMD, LSTM, FXCM, PAQ8, 47 mixers, SSE); no replayed inputs",
-              "streams_per_gpu": S, "step_bytes_per_stream": B,
+              "streams_per_gpu": S, "step_bytes_per_stream": B, "ppmd_arena_mb": int(os.environ["CMIXB200_PPMD_MB"]),
               "parallelism": "independent files sharded over %d rank(s), no data-path collective" % max(world, args.gpus),
               "l2": "inputs larger than L2: every coded byte walks ~22 GB of per-stream HBM tables (hashed buckets of ~330 contexts, 40 mixer weight sets)"}
 
@@ -179,16 +188,16 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n_e2e = N_E2E
-    total_steps = file_bytes(B, W, K) // B
+    total_steps = (file_bytes(B, W, K) + 5) // B
     S_total = max(S, args.aggregate_streams)
     free0 = torch.cuda.mem_get_info(dev)[0]
     streams = []
     for s in stream_block(S_total * world, world, rank):
         if len(streams) >= S_total:
             break
-        text = bench_text(B * total_steps, stream_id=s)
+        text = bench_stream(file_bytes(B, W, K), stream_id=s)
         vocab = np.ones(256, dtype=np.uint8)
-        if text.size >= 10000:                               # runner.cpp:14,197: short files keep the full symbol set
+        if text.size >= 10000:                               # runner.cpp:14,197: short streams keep the full symbol set
             vocab[:] = 0
             vocab[np.unique(text)] = 1
         P = cmix_b200.Predictor(vocab, device=local_rank)

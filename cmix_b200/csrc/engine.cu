@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -564,13 +565,23 @@ int BuildStream(cmixb200_predictor* P) {
   TRY(P->Alloc(&P->d_st, 1));
   // ---------------- PPMD (ppmd_model.h): model registers + three flat arenas ----------------
   {
+    // The reference gives its PPMD model a 14 000 MB heap (predictor.cpp:101). Default: the same budget when a quarter of the
+    // free HBM covers it, else that quarter (>= 64 MB); CMIXB200_PPMD_MB overrides. Text positions share the successor word
+    // with context references (below PPMD_CTX_BASE), so the text arena stops short of 1 GiB and the rest goes to the states.
     const char* mb_env = getenv("CMIXB200_PPMD_MB");
-    const size_t mb = mb_env ? (size_t)atol(mb_env) : 32;           // 32 MB: ~0.5 M contexts, roughly 150-500 KB of input
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t mb = mb_env ? (size_t)atol(mb_env) : std::min<size_t>(14000, free_b / 4 >> 20);
+    if (mb < 64) mb = 64;
     PpmdModel pm;
     memset(&pm, 0, sizeof pm);
-    pm.ctx_cap = (uint32_t)(mb * (1u << 20) / 4 / sizeof(PpmdCtx));
-    pm.pool_cap = (uint32_t)(mb * (1u << 20) / 2 / sizeof(PpmdSt));
-    pm.text_cap = (uint32_t)(mb * (1u << 20) / 4);
+    const size_t bytes = mb << 20;
+    const size_t text_b = std::min<size_t>(bytes / 4, (size_t)PPMD_CTX_BASE - 4096);
+    const size_t ctx_b = bytes / 4;
+    const size_t pool_b = bytes - text_b - ctx_b;
+    pm.ctx_cap = (uint32_t)std::min<size_t>(ctx_b / sizeof(PpmdCtx), 0x7fffffffu);
+    pm.pool_cap = (uint32_t)std::min<size_t>(pool_b / sizeof(PpmdSt), 0xfffffff0u);
+    pm.text_cap = (uint32_t)text_b;
     TRY(P->Alloc(&pm.ctx, pm.ctx_cap, false));
     TRY(P->Alloc(&pm.pool, pm.pool_cap, false));
     TRY(P->Alloc(&pm.text, pm.text_cap, false));
@@ -636,6 +647,8 @@ void HarvestMixTimes(cmixb200_predictor* P) {
 
 // Launch the bulk kernels of one sub-chunk for a batch of streams whose ChunkArgs are already on the device:
 // ppmd -> (small | lstm -> fxcm) -> mix [-> encode], each on its own CUDA stream of the group's lead predictor.
+int CheckPaq8(cmixb200_predictor* P);
+
 int LaunchChunk(cmixb200_predictor* lead, ChunkArgs* d_args, int n_streams, bool pretrain, bool with_coder = false,
                 bool with_ppmd = false, bool with_fx = false, bool with_p8 = false) {
   const Tables T = lead->T;
@@ -819,6 +832,18 @@ int RunPipelined(cmixb200_predictor** preds, int n_streams, const u8* const* d_b
       if (err) { g_last_error = "PPMD arena exhausted: raise CMIXB200_PPMD_MB (the reference would cut its model off here)"; return CMIXB200_ERR_CAPACITY; }
     }
   }
+  if (any_p8) for (int s = 0; s < n_streams; ++s) TRY(CheckPaq8(preds[s]));
+  return CMIXB200_OK;
+}
+
+// PAQ8's sticky error word: a block the resident model does not cover (the reference would switch to its image / audio / JPEG
+// models there) or two mixer selectors on one weight set. The stream's predictions are no longer the reference's.
+int CheckPaq8(cmixb200_predictor* P) {
+  if (!P->d_p8) return CMIXB200_OK;
+  uint32_t err = 0;
+  CK(cudaMemcpy(&err, (const char*)P->d_p8 + offsetof(p8::State, error), 4, cudaMemcpyDeviceToHost));
+  if (err & p8::ERR_UNSUPPORTED_BLOCK) { g_last_error = "PAQ8: the stream holds an image / audio / JPEG block; those sub-models are not resident (replay the PAQ8 inputs: CMIXB200_REPLAY_PAQ8)"; return CMIXB200_ERR_UNSUPPORTED; }
+  if (err) { g_last_error = "PAQ8: two mixer selectors met on one weight set"; return CMIXB200_ERR_UNSUPPORTED; }
   return CMIXB200_OK;
 }
 
@@ -964,6 +989,16 @@ float cmixb200_predict(cmixb200_predictor* P) {
   cudaError_t e = cudaMemcpyAsync(&p, &P->d_st->last_p, 4, cudaMemcpyDeviceToHost, P->s_mix);
   if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
   if (e != cudaSuccess) { g_last_error = std::string("predict: ") + cudaGetErrorString(e); return -1.0f; }
+  if (P->bit_context == 1 && P->bits_done) {   // once per byte: the sticky error words of the resident models (s_mix is idle here)
+    if (CheckPaq8(P) != CMIXB200_OK) return -1.0f;
+    if (!P->ppmd_byte_valid || P->d_ppmd_model) {
+      uint32_t err = 0;
+      if (P->d_ppmd_model && cudaMemcpy(&err, (const char*)P->d_ppmd_model + offsetof(PpmdModel, error), 4, cudaMemcpyDeviceToHost) == cudaSuccess && err) {
+        g_last_error = "PPMD arena exhausted: raise CMIXB200_PPMD_MB (the reference would cut its model off here)";
+        return -1.0f;
+      }
+    }
+  }
   if (P->ext_bit_valid) {   // replayed slots fall back to "0.5" until they are fed again
     const size_t first = P->d_fx ? fx::N_OUT : 0, last = P->d_p8 ? (size_t)fx::N_OUT : (size_t)N_EXT;
     if (last > first) cudaMemsetAsync(P->d_ext_bit + first, 0xFF, (last - first) * 2, P->s_mix);
@@ -1176,6 +1211,14 @@ int cmixb200_debug_fetch(cmixb200_predictor* P, int what, void* out, size_t byte
       if (!P->d_ext_gen || bytes > P->ext_gen_bits * N_EXT * 2) { g_last_error = "debug_fetch: no generated codes of that size"; return CMIXB200_ERR_ARG; }
       src = P->d_ext_gen; break;
     case CMIXB200_DBG_EXT_BIT: src = P->d_ext_bit; break;
+    case CMIXB200_DBG_PPMD_USAGE: {
+      PpmdModel pm;
+      if (bytes < 6 * 4) { g_last_error = "debug_fetch: PPMD usage is 6 u32"; return CMIXB200_ERR_ARG; }
+      CK(cudaMemcpy(&pm, P->d_ppmd_model, sizeof pm, cudaMemcpyDeviceToHost));
+      const uint32_t u[6] = {pm.ctx_top, pm.ctx_cap, pm.pool_top, pm.pool_cap, pm.text_pos, pm.text_cap};
+      memcpy(out, u, sizeof u);
+      return CMIXB200_OK;
+    }
     case CMIXB200_DBG_PROFILE:
       if (!P->d_prof) { CK(cudaMalloc(&P->d_prof, 64 * 8)); CK(cudaMemset(P->d_prof, 0, 64 * 8)); }
       src = P->d_prof; break;

@@ -60,6 +60,7 @@ __device__ __forceinline__ u32 ppmd_scale(u32 cum, u32 freq, u32 total) {
 // are done in one pass, and only the escape chain (one scaling per context) stays serial. Integer arithmetic
 // throughout: the result is the same sqp[256]; tests compare the device against the reference's dumps.
 __device__ void ppmd_prepare_byte_warp(PpmdModel& m, int lane) {
+  if (m.error) return;                       // frozen after an exhausted arena (uniform across the warp: lane 0 set it before the barrier)
   for (int i = lane; i < 256; i += 32) m.sqp[i] = 0;
   const int saved_fall = m.order_fall;
   int order_fall = saved_fall, num_masked = 0;

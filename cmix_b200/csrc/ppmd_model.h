@@ -526,6 +526,7 @@ PP_HD uint32_t pp_update_model(PpmdModel& m, uint32_t min_ref) {
 
 // ppmd_UpdateByte (ppmd.cpp:1283-1314)
 PP_HD void ppmd_update_byte(PpmdModel& m, int c) {
+  if (m.error) return;                       // arena exhausted earlier: the model is frozen, the engine reports CMIXB200_ERR_CAPACITY
   uint32_t minc = m.max_context;
   if (pp_ctx(m, minc).ns) pp_symbol1(m, pp_ctx(m, minc), c); else pp_bin_symbol(m, pp_ctx(m, minc), c);
   while (m.found == PPMD_NIL) {
@@ -550,6 +551,7 @@ PP_HD void pp_sq_store(PpmdModel& m, uint32_t sym, uint32_t freq, uint32_t total
 
 // ppmd_PrepareByte + ConvertSQ (ppmd.cpp:1256-1281, 1116-1140): fills m.sqp[256].
 PP_HD void ppmd_prepare_byte(PpmdModel& m) {
+  if (m.error) return;
   m.sq_n = 0; m.num_masked = 0;
   const int saved_fall = m.order_fall;
   uint32_t minc = m.max_context - PPMD_CTX_BASE;

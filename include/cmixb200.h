@@ -23,7 +23,8 @@ extern "C" {
 #endif
 
 enum { CMIXB200_OK = 0, CMIXB200_ERR_CUDA = 1, CMIXB200_ERR_ARG = 2,
-       CMIXB200_ERR_CAPACITY = 3 /* a model arena is full (PPMD: raise CMIXB200_PPMD_MB); the stream is unusable */ };
+       CMIXB200_ERR_CAPACITY = 3 /* a model arena is full (PPMD: raise CMIXB200_PPMD_MB); the stream is unusable */,
+       CMIXB200_ERR_UNSUPPORTED = 4 /* the resident PAQ8 met an image / audio / JPEG block it does not model; the stream is unusable */ };
 
 enum {
   CMIXB200_N_EXT = 2022,  /* replayed FXCM (431) + PAQ8 (1591) outputs per bit, as 12-bit codes k
@@ -106,6 +107,7 @@ enum { CMIXB200_DBG_SMALL_X = 1, CMIXB200_DBG_SEL = 2, CMIXB200_DBG_LSTM_X = 3, 
        CMIXB200_DBG_PPMD_PROFILE = 9 /* 6 u64: cycles in symbol search, model update, suffix walk, ConvertSQ, emit; bytes */,
        CMIXB200_DBG_EXT_GEN = 10 /* [n_bytes*8][2022] u16: the codes the resident models wrote in the last bulk piece (<= 2048 bytes) */,
        CMIXB200_DBG_EXT_BIT = 11 /* [2022] u16: lock-step codes for the next Predict() */,
+       CMIXB200_DBG_PPMD_USAGE = 12 /* 6 u32: contexts used / capacity, states used / capacity, text bytes used / capacity */,
        CMIXB200_DBG_PPMD_BULK = 8 /* [n_bytes][256] f32: the distributions the resident model produced in the last bulk call */ };
 int cmixb200_debug_fetch(cmixb200_predictor*, int what, void* out, size_t bytes);
 
