@@ -38,8 +38,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-NCU_DRAM_BYTES_PER_BIT = 34786      # mix_kernel_v3: (63.16 MB read + 8.09 MB written) / 2048 bits, ncu --set full, profiles/r01_ncu_full_metrics.csv
-ALGO_BYTES_PER_BIT = 450_000        # 55 172 fp32 weights read + written, + input vectors
+# algorithmic bytes per coded bit and ncu's DRAM bytes per coded bit of one launch (profiles/)
+ALGO_BYTES_PER_BIT = {
+    "mix_kernel_v3": 450_000,       # 55 172 fp32 weights read + written, + input vectors
+    "paq8_kernel": 212_000,         # 28 selected int16 weight sets x 1552 read + written (174 KB) + ~273 live contexts x (64 B bucket line r/w + StateMap cells)
+    "fxcm_kernel": 34_000,          # 10 selected weight rows x 512 int16 read + written (20 KB) + ~100 live contexts x 140 B
+}
+NCU_DRAM_BYTES_PER_BIT = {
+    "mix_kernel_v3": 34_786,        # profiles/r01_ncu_full_metrics.csv: (63.16 MB + 8.09 MB) / 2048 bits
+    "paq8_kernel": 22_483,          # profiles/r02_ncu_producers.txt: (22.28 MB + 0.74 MB) / 1024 bits (weight sets stay in shared memory)
+    "fxcm_kernel": 4_100,           # profiles/r02_ncu_producers.txt
+}
 KERNELS = ["mix_kernel_v3", "small_kernel", "lstm_kernel", "ppmd_kernel", "fxcm_kernel", "paq8_kernel"]
 SEED = 0xE9E80001
 
@@ -312,11 +321,18 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         n_bits = S * B * K * 8
-        mix_ms, mix_n = kms.get("mix_kernel_v3", (0.0, 0))
-        bits_per_launch = n_bits / max(mix_n, 1)
-        achieved = ALGO_BYTES_PER_BIT * bits_per_launch / (mix_ms / max(mix_n, 1) / 1e3) / 1e9 if mix_ms > 0 else None
         per_bit = {k: (v[0] * 1e3 / n_bits if n_bits else None) for k, v in kms.items()}      # us per coded bit (kernels overlap on their own streams)
         pole = max(per_bit, key=lambda k: per_bit[k] or 0) if per_bit else None
+        roof = {}
+        for kname in ("paq8_kernel", "fxcm_kernel", "mix_kernel_v3"):
+            ms, n = kms.get(kname, (0.0, 0))
+            if ms <= 0 or n == 0:
+                continue
+            bits_per_launch = n_bits / n
+            ach = ALGO_BYTES_PER_BIT[kname] * bits_per_launch / (ms / n / 1e3) / 1e9
+            roof[kname] = {"achieved": ach, "frac": ach / peak, "launches": n, "ms_total": ms, "bits_per_launch": bits_per_launch,
+                           "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT[kname], "traffic": NCU_DRAM_BYTES_PER_BIT[kname] * bits_per_launch}
+        dom = pole if pole in roof else "mix_kernel_v3"
         p_dev = head[0]["d_out"][W * B * 8:(W + K) * B * 8].cpu().numpy().astype(np.float64)
         bits_coded = np.unpackbits(head[0]["text"][W * B:(W + K) * B])
         out = {
@@ -326,12 +342,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": S * B, "d2h_bytes_per_step": S * B * 8 * 4, "steps": n_e2e,
                     "note": "cmixb200_code_batch with pinned host buffers: the step's bytes go up and its probabilities come back inside the timed region (bytes per rank per step)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "mix_kernel_v3", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": NCU_DRAM_BYTES_PER_BIT * bits_per_launch, "traffic_unit": "B per launch",
-                         "traffic_source": "profiles/r01_ncu_full_metrics.csv: dram read+write of one mix_kernel_v3 launch / its 2048 bits (rows stay in shared memory)",
-                         "frac_dram": (NCU_DRAM_BYTES_PER_BIT / ALGO_BYTES_PER_BIT * achieved / peak) if achieved else None,
-                         "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind, "algorithmic_bytes_per_bit": ALGO_BYTES_PER_BIT, "mix_kernel_ms_total": mix_ms, "mix_launches": mix_n,
-                         "note": "latency bound, not bandwidth bound: every dot product is one serial fp32 FADD chain (bit-exact parity); frac_dram is the fraction of the HBM peak the kernel's measured DRAM traffic amounts to"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": roof[dom]["achieved"], "peak": peak, "unit": "GB/s", "frac": roof[dom]["frac"],
+                         "traffic": roof[dom]["traffic"], "traffic_unit": "B per launch",
+                         "traffic_source": "ncu --set full DRAM read+write of one launch per coded bit (profiles/r02_ncu_producers.txt, r01_ncu_full_metrics.csv) x bits per launch",
+                         "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind, "per_kernel": roof,
+                         "note": "the dominant kernel is the one the stream waits for (longest CUDA-event time per coded bit). Every kernel of this path is LATENCY bound, "
+                                 "not bandwidth bound: bit t+1 cannot start before bit t is perceived, the integer models walk dependent hash-bucket chains and every "
+                                 "fp32 dot product is one serial FADD chain (bit-exact parity), so the HBM fraction is small by construction"},
             "kernels": {"us_per_coded_bit": per_bit, "pole": pole, "note": "CUDA events on each kernel's own stream; the kernels of a sub-chunk overlap, the stream advances at the pole's pace"},
             "single_stream": {"MB_per_s": value / max(S * world, 1), "hours_per_100MB": 100.0 / max(value / max(S * world, 1), 1e-12) / 3600.0},
             "aggregate": aggregate,
