@@ -289,11 +289,11 @@ __device__ __noinline__ void p8_probe_single(P8Shared& sh, int tid, int y, int c
   else if (tid == P8_TID_MATCH) { Out o = p8_out(sh, sh.unit_off[7]); match_core(S, o); }
   else if (tid == P8_TID_MATCH + 1) { if (bpos != 0) record_pre(S); }   // on a byte boundary it follows record_byte (round 2)
   else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 10) sh.dmc_st[tid - P8_TID_W10] = dmc_st(T, S.dmc[tid - P8_TID_W10], y);
-  else if (tid >= P8_TID_W10 + 10 && tid < P8_TID_W10 + 13) {
-    const int r = tid - (P8_TID_W10 + 10);
+  else if (tid >= P8_TID_MATCH + 2 && tid < P8_TID_MATCH + 5) {
+    const int r = tid - (P8_TID_MATCH + 2);
     Out o = p8_out(sh, sh.unit_off[4 + r]);
     rcm_mix(r == 0 ? S.rcm7 : r == 1 ? S.rcm9 : S.rcm10, o, c0, bpos);
-  } else if (tid >= P8_TID_W10 + 13 && tid < P8_TID_W10 + 18) { const int r = tid - (P8_TID_W10 + 13); Out o = p8_out(sh, sh.unit_off[48 + r]); linear_small(S, o, r); }
+  } else if (tid >= P8_TID_W11 + 4 && tid < P8_TID_W11 + 9) { const int r = tid - (P8_TID_W11 + 4); Out o = p8_out(sh, sh.unit_off[48 + r]); linear_small(S, o, r); }
   else if (tid == P8_TID_W11) { Out o = p8_out(sh, sh.unit_off[8]); smatch_head(S, o); }
   else if (tid == P8_TID_W11 + 1 || tid == P8_TID_W11 + 2) {
     const int r = tid - (P8_TID_W11 + 1);
@@ -379,13 +379,6 @@ __device__ __noinline__ void p8_apply_small(P8Shared& sh, int tid, int y, int bp
   if (tid >= P8_TID_MATCH && tid < P8_TID_MATCH + 9) {   // the nine maps behind the match model
     Out o = p8_out(sh, sh.unit_off[7]);
     match_unit(S, o, tid - P8_TID_MATCH);
-  } else if (tid == P8_TID_MATCH + 9) {                    // ModelStats and the 19 selector sets that do not wait for the order-N map
-    xml_stats(S);
-    S.m.nx = sh.unit_off[P8_N_UNITS];
-    smatch_select(S);
-    record_select(S);
-    text_select(S);
-    exe_select(S);
   } else if (tid >= P8_TID_W10 && tid < P8_TID_W10 + 12) {   // the record model's 12 direct maps (contexts selected by record_pre)
     Out o = p8_out(sh, sh.unit_off[24 + (tid - P8_TID_W10)]);
     record_small(S, o, tid - P8_TID_W10);
@@ -484,6 +477,10 @@ __device__ __forceinline__ void p8_row_store(short* dst, const short* src, int l
 }
 static_assert(p8::N_IN % 8 == 0 && p8::N_IN / 8 <= 7 * 32, "a weight row is at most 7 16-byte words per lane");
 
+// named barrier 2: the model warps signal "the state the 19 order-independent selector sets read is final" (arrive), the
+// first SGD warp waits for it (sync) and computes those sets beside the apply phase
+__device__ __forceinline__ void p8_signal_selects() { asm volatile("bar.arrive 2, 416;" ::: "memory"); }
+__device__ __forceinline__ void p8_await_selects() { asm volatile("bar.sync 2, 416;" ::: "memory"); }
 __device__ __forceinline__ void p8_sync_maps() { asm volatile("bar.sync 1, 384;" ::: "memory"); static_assert(P8_MAP_THREADS == 384, "named barrier width"); }
 
 // Mixer::update for the 28 cached weight sets selected for the previous bit, by the four SGD warps (tid 0..127 of them)
@@ -551,8 +548,21 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit 
   P8_T(0);
   const int bpos = S.bpos, c0 = S.c0;
   const bool byte_start = bpos == 0;
-  if (tid >= P8_MAP_THREADS) p8_sgd(sh, tid - P8_MAP_THREADS);
-  else {
+  if (tid >= P8_MAP_THREADS) {
+    p8_sgd(sh, tid - P8_MAP_THREADS);
+    if (warp == P8_MAP_WARPS) {            // ModelStats and the 19 selector sets that do not wait for the order-N map
+      p8_await_selects();
+      if (lane == 0) {
+        xml_stats(S);
+        smatch_select(S);
+        record_select(S);
+        text_select(S);
+        exe_select(S);
+        if (S.m.ncxt != MAIN_SET_FIRST || S.m.base != MAIN_SET_BASE) S.error |= ERR_MIXER_ALIAS;
+        S.m.ncxt = N_SETS;
+      }
+    }
+  } else {
     if (tid == 0) { S.m.nx = S.m.base = S.m.ncxt = 0; }
     if (byte_start) {
       // ---- byte boundary, round 1: context computation, one model per lane / warp
@@ -608,6 +618,7 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit 
       }
       for (int k = tid; k < P8_SEEN; k += P8_MAP_THREADS) sh.u.seen[k] = 0ull;
       p8_sync_maps();
+      p8_signal_selects();
       P8_T(5);
       if (warp < 7) p8_probe_cm(sh, tid, y, c0, bpos);
       p8_sync_maps();
@@ -628,6 +639,7 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit 
         if (lane == 0) P8_M(24 + warp);
       }
       p8_sync_maps();
+      p8_signal_selects();
       P8_T(3);
       if (sh.any_clash) { p8_number(sh, tid, y, c0, bpos); p8_sync_maps(); }
       P8_T(7);
@@ -647,8 +659,9 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit 
         for (int k = 0; k < P8_N_CM; ++k) if (!sh.clash[k]) p8_cm(S, k).cn = 0;
         for (int k = 0; k < P8_N_CM2; ++k) p8_cm2(S, k).index = 0;
       }
-      main_select(S, sh.res2[0]);
+      main_select_fixed(S, sh.res2[0]);      // sets 19..27; the first SGD warp writes 0..18 (and the count) beside this
       Mixer& m = S.m;
+      m.nx = sh.unit_off[P8_N_UNITS];
       m.n2 = m.nx;
       while (m.nx & 7) m.tx[m.nx++] = 0;
     }

@@ -623,6 +623,11 @@ P8_HD inline int dmc_st(const Tables& T, Dmc& d, int y) {
     d.curr = y == 0 ? cur.nx0 >> 4 : cur.nx1 >> 4;
   }
   const DmcNode& c = t[d.curr];
+#if defined(__CUDA_ARCH__)
+  // the node the next bit moves to is one of the two children: have both lines on their way
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (c.nx0 >> 4)));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (c.nx1 >> 4)));
+#endif
   const u32 n0 = c.c0 + 1u, n1 = c.c1 + 1u;
   const int pr1 = (int)((n1 << 12) / (n0 + n1));
   const int pr2 = sm32_p(T, d.sm, y, dmc_state(c), 256);

@@ -780,6 +780,31 @@ P8_HD inline void main_select(State& S, int order) {   // the nine selector sets
   mset(m, c0, 256);
 }
 
+// The same nine sets written at their fixed places: the 19 sets before them always cover MAIN_SET_BASE weight sets, so a lane can
+// compute these while another one is still producing the first 19 (paq8.cuh).
+enum { MAIN_SET_FIRST = 19, MAIN_SET_BASE = 66656 };
+static_assert(MAIN_SET_BASE + 64 + 4 * 1536 + 2 * 2048 + 2 * 256 == N_WSETS && MAIN_SET_FIRST + 9 == N_SETS, "selector layout");
+P8_HD inline void main_select_fixed(State& S, int order) {
+  Mixer& m = S.m;
+  const int bpos = S.bpos, c0 = S.c0;
+  int* cx = m.cxt + MAIN_SET_FIRST;
+  int base = MAIN_SET_BASE;
+  cx[0] = base + ((imax(0, order - 3) << 3) | bpos); base += 64;
+  order = imax(0, order - 5);
+  const u32 d = (u32)c0 << (8 - bpos);
+  u32 c = (d + (bpos == 1 ? S.b3 / 2 : 0)) & 192;
+  if (!bpos) c = S.words * 16 & 192;
+  const u32 c1 = (u32)buf(S, 1);
+  cx[1] = base + (int)((u32)order * 256 + (S.w4 & 240) + (S.b2 >> 4)); base += 1536;
+  cx[2] = base + (int)((u32)order * 256 + (S.w4 & 3) * 64 + (S.words >> 1 & 63)); base += 1536;
+  cx[3] = base + (int)((u32)bpos * 256 + c1); base += 2048;
+  cx[4] = base + (int)((u32)imin(bpos, 5) * 256 + (S.tt & 63) + c); base += 1536;
+  cx[5] = base + (int)((u32)order * 256 + ((d | c1 >> bpos) & 248) + (u32)bpos); base += 1536;
+  cx[6] = base + (int)((u32)bpos * 256 + (((S.words << bpos & 255) >> bpos) | (d & 255))); base += 2048;
+  cx[7] = base + S.last_prediction / 16; base += 256;
+  cx[8] = base + c0;
+}
+
 P8_HD inline int context_model(State& S) {
   const Tables& T = *S.T;
   const int y = S.y, bpos = S.bpos;
