@@ -299,6 +299,12 @@ FX_HD inline u32 map_ctx_bit(State& S, int id, int i, const Out& unit) {
     }
     s = m.t[m.cp[i]];
   }
+#if defined(__CUDA_ARCH__)
+  if ((bp == 1 || bp == 4) && m.cp[i] != FX_NULL) {   // the bucket of the next bit is one of two neighbours: start both loads now
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(m.t + ((size_t)((m.cxt[i] + (u32)cc * 2) & m.tmask) << sh)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(m.t + ((size_t)((m.cxt[i] + (u32)cc * 2 + 1) & m.tmask) << sh)));
+  }
+#endif
   if (s == 0) {
     emit(T, o, 0); if (sp.skip2) emit(T, o, 0); emit(T, o, 0); emit(T, o, 0); emit(T, o, 64, false);
   } else {

@@ -239,6 +239,15 @@ template <class T> P8_HD inline T ictx_get(const ICtx<T>& c) { return c.data[c.c
 struct Rnd { u32 table[64]; int i; };
 P8_HD inline u32 rnd_next(Rnd& r) { ++r.i; return r.table[r.i & 63] = r.table[(r.i - 24) & 63] ^ r.table[(r.i - 55) & 63]; }
 
+// The bucket a context moves to on the next bit is one of two neighbours (its index ends in the next coded bit): start both loads now.
+P8_HD inline void bucket_prefetch2(const u8* t, u32 mask, u32 ctx, u32 add2) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t + ((size_t)((ctx + add2) & mask) << 6)));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t + ((size_t)((ctx + add2 + 1) & mask) << 6)));
+#else
+  (void)t; (void)mask; (void)ctx; (void)add2;
+#endif
+}
 // bucket probe shared by both map flavours (ContextMap::E::get :1038-1047, Bucket::Find :1174-1190): returns the offset of bh[slot][0]
 P8_HD inline int bucket_find(u8* t, u32 bucket, u16 ch) {
   u8* e = t + ((size_t)bucket << 6);
@@ -337,6 +346,7 @@ P8_HD inline int cm_step(Cm& m, int i, Out& o, int ns, int y, int c0, int bp, in
       } break;
     }
   }
+  if ((bp == 1 || bp == 4) && m.cp[i] != P8_NULL) bucket_prefetch2(t, m.mask, m.cxt[i], (u32)c0 * 2);
   const u8* rp = t + m.runp[i];
   const int rc = rp[0];
   if (((rp[1] + 256) >> (8 - bp)) == c0) {
@@ -427,6 +437,7 @@ P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
       case 4: case 7: m.bs[i] = m.bs0[i] + 3 + (int)(m.bits & 3); break;
     }
   }
+  if ((bpos == 1 || bpos == 4) && m.bs[i] != P8_NULL) bucket_prefetch2(t, m.mask, m.cxt[i], m.bits * 2);
   int state = m.bs[i] != P8_NULL ? t[m.bs[i]] : 0;
   const int result = state > 0;
   const u8* h = t + m.bh[i];
