@@ -69,6 +69,7 @@ def load_library():
     lib.cmixb200_coder_begin.argtypes = [vp, c.c_size_t]
     lib.cmixb200_coder_finish.argtypes = [vp, vp, c.c_size_t, c.POINTER(c.c_size_t)]
     lib.cmixb200_pretrain_bytes.argtypes = [vp, vp, c.c_size_t]
+    lib.cmixb200_decode_bytes.argtypes = [vp, vp, c.c_size_t, vp, c.c_size_t]
     lib.cmixb200_last_error.restype = c.c_char_p
     lib.cmixb200_kernel_launches.argtypes = [vp]
     lib.cmixb200_kernel_launches.restype = c.c_ulonglong
@@ -180,6 +181,13 @@ class Predictor:
         n = ctypes.c_size_t(0)
         _check(self._lib, self._lib.cmixb200_coder_finish(self._h, out.ctypes.data, out.size, ctypes.byref(n)), "coder_finish")
         return out[:n.value].tobytes()
+
+    def decode_bytes(self, archive, n_bytes):
+        """Decoder::Decode on the device: n_bytes of the stream from the arithmetic-coded archive body."""
+        arch = np.ascontiguousarray(np.frombuffer(bytes(archive), dtype=np.uint8))
+        out = np.empty(int(n_bytes), dtype=np.uint8)
+        _check(self._lib, self._lib.cmixb200_decode_bytes(self._h, arch.ctypes.data, arch.size, out.ctypes.data, out.size), "decode_bytes")
+        return out
 
     def pretrain_bytes(self, data):
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))

@@ -45,5 +45,33 @@ __global__ void encode_flush_kernel(CoderState* cs) {                 // Encoder
   *cs = c;
 }
 
+// One step of Decoder::Decode (reference src/coder/decoder.cpp:16-39) between the predict and the perceive kernels of a bit, on
+// the device: the probability never leaves HBM and the decoded bit is handed to the perceive kernels through DecodeState.
+__device__ __forceinline__ u32 decoder_read_byte(DecodeState& d) { return d.pos < d.n_arch ? d.arch[d.pos++] : 0u; }   // decoder.cpp:10-14
+__global__ void decode_begin_kernel(DecodeState* ds) {                // Decoder::Decoder, decoder.cpp:3-8
+  DecodeState d = *ds;
+  d.x1 = 0; d.x2 = 0xffffffffu; d.x = 0; d.ctx = 1; d.t = 0; d.bit = d.full = 0;
+  for (int i = 0; i < 4; ++i) d.x = (d.x << 8) + (decoder_read_byte(d) & 0xff);
+  *ds = d;
+}
+__global__ void decode_step_kernel(const StreamState* st, DecodeState* ds) {
+  DecodeState d = *ds;
+  const u32 p = (u32)XM_FADD(1.0f, XM_FMUL(65534.0f, st->last_p));   // Decoder::Discretize, decoder.cpp:16-18
+  const u32 range = d.x2 - d.x1;
+  const u32 xmid = d.x1 + (range >> 16) * p + (((range & 0xffffu) * p) >> 16);
+  u32 bit = 0;
+  if (d.x <= xmid) { bit = 1; d.x2 = xmid; } else d.x1 = xmid + 1;
+  while (((d.x1 ^ d.x2) & 0xff000000u) == 0) {
+    d.x1 <<= 8;
+    d.x2 = (d.x2 << 8) + 255;
+    d.x = (d.x << 8) + decoder_read_byte(d);
+  }
+  d.bit = bit;
+  d.ctx = d.ctx * 2 + bit;
+  if (d.ctx >= 256) { d.full = d.ctx & 255; d.out[d.t >> 3] = (u8)d.full; d.ctx = 1; }
+  d.t += 1;
+  *ds = d;
+}
+
 }  // namespace cmixb200
 #endif

@@ -290,7 +290,7 @@ struct cmixb200_predictor {
   // device arithmetic coder (compress direction)
   cudaStream_t s_ppmd = nullptr; float* d_ppmd_gen = nullptr; size_t ppmd_gen_bytes = 0;   // resident PPMD: own stream, scratch [n_bytes][256]
   PpmdModel* d_ppmd_model = nullptr;
-  cudaEvent_t ev_lock_mix = nullptr, ev_lock_small = nullptr;   // lock-step: order the two library streams per bit
+  cudaEvent_t ev_lock_mix = nullptr, ev_lock_small = nullptr, ev_lock_p8 = nullptr, ev_lock_bit = nullptr;   // lock-step: order the library streams per bit
   CoderState* d_coder = nullptr; u8* d_code = nullptr; size_t code_cap = 0; bool coder_on = false;
   // lock-step state
   u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
@@ -916,6 +916,8 @@ int cmixb200_create_ex(const uint8_t vocab[256], const char* dictionary_path, in
     cudaStreamCreateWithPriority(&P->s_p8, cudaStreamNonBlocking, p_small);
     cudaEventCreateWithFlags(&P->ev_lock_mix, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_lock_small, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_lock_p8, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_lock_bit, cudaEventDisableTiming);
     cudaEventRecord(P->ev_lock_mix, P->s_mix);
     if (cudaMalloc(&P->d_ext_bit, N_EXT * 2) != cudaSuccess ||
         cudaMalloc(&P->d_ppmd_byte, 256 * 4) != cudaSuccess) r = CMIXB200_ERR_CUDA;
@@ -938,6 +940,8 @@ void cmixb200_destroy(cmixb200_predictor* P) {
     for (void* q : {(void*)P->d_bytes2[k], (void*)P->d_ext2[k], (void*)P->d_ppmd2[k]}) if (q) cudaFree(q);
   if (P->ev_lock_mix) cudaEventDestroy(P->ev_lock_mix);
   if (P->ev_lock_small) cudaEventDestroy(P->ev_lock_small);
+  if (P->ev_lock_p8) cudaEventDestroy(P->ev_lock_p8);
+  if (P->ev_lock_bit) cudaEventDestroy(P->ev_lock_bit);
   if (P->d_coder) cudaFree(P->d_coder);
   if (P->d_code) cudaFree(P->d_code);
   if (P->s_ppmd) cudaStreamDestroy(P->s_ppmd);
@@ -973,18 +977,25 @@ int cmixb200_feed_external_byte(cmixb200_predictor* P, const float* ppmd256) {
   return CMIXB200_OK;
 }
 
-float cmixb200_predict(cmixb200_predictor* P) {
+// The three predict launches of a bit: producers (small models || LSTM read-out) on s_small behind the previous small_perceive
+// and the previous bit's mixer / LSTM update, then 26 row CTAs (one serial chain each) and the final stage on s_mix behind the
+// producers and the previous bit's PAQ8 update (s_p8).
+static int LaunchPredict(cmixb200_predictor* P) {
   const Tables T = P->T;
-  if (cudaSetDevice(P->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1.0f; }
-  // 3 launches: producers (small models || LSTM read-out), 26 row CTAs (one serial chain each), final stage
-  // the producers run on s_small (behind the previous small_perceive), after the previous bit's mixer/LSTM update
-  if (cudaStreamWaitEvent(P->s_small, P->ev_lock_mix, 0) != cudaSuccess) { g_last_error = "predict: event wait failed"; return -1.0f; }
+  CK(cudaStreamWaitEvent(P->s_small, P->ev_lock_mix, 0));
   lock_predict_inputs_kernel<<<2, 64, 0, P->s_small>>>(P->d_st, T);
-  cudaEventRecord(P->ev_lock_small, P->s_small);
-  cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0);
+  CK(cudaEventRecord(P->ev_lock_small, P->s_small));
+  CK(cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0));
+  if (P->d_p8) CK(cudaStreamWaitEvent(P->s_mix, P->ev_lock_p8, 0));
   mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, (P->ext_bit_valid || P->d_fx || P->d_p8) ? P->d_ext_bit : nullptr);
   mix_predict_final_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T);
   P->launches += 3;
+  return CMIXB200_OK;
+}
+
+float cmixb200_predict(cmixb200_predictor* P) {
+  if (cudaSetDevice(P->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return -1.0f; }
+  if (LaunchPredict(P) != CMIXB200_OK) return -1.0f;
   float p = -1.0f;
   cudaError_t e = cudaMemcpyAsync(&p, &P->d_st->last_p, 4, cudaMemcpyDeviceToHost, P->s_mix);
   if (e == cudaSuccess) e = cudaStreamSynchronize(P->s_mix);      // also surfaces errors of the previous Perceive()
@@ -1007,35 +1018,102 @@ float cmixb200_predict(cmixb200_predictor* P) {
   return p;
 }
 
+// The perceive launches of a bit. `dbit` (device, {bit, completed byte}) replaces the host's bit in a decode loop; byte_done is
+// positional either way. Queued, not awaited: the next predict launches are ordered behind them by events.
+static int LaunchPerceive(cmixb200_predictor* P, int bit, u32 full, bool byte_done, const u32* dbit) {
+  const float* ppmd = byte_done ? P->d_ppmd_byte : nullptr;
+  float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
+  if (dbit) {                                    // the decoded bit is produced on s_mix
+    CK(cudaEventRecord(P->ev_lock_bit, P->s_mix));
+    CK(cudaStreamWaitEvent(P->s_small, P->ev_lock_bit, 0));
+    if (P->s_p8) CK(cudaStreamWaitEvent(P->s_p8, P->ev_lock_bit, 0));
+  }
+  if (byte_done && !P->ppmd_byte_valid) {
+    // no replayed distribution for this byte: the resident PPMD model is updated and emits it (ppmd.cpp:1328-1338)
+    ppmd_byte_kernel<<<1, 32, sizeof(PpmdWarpShared), P->s_small>>>(P->d_st, full, P->d_ppmd_byte, dbit);
+    P->launches++;
+    CK(cudaEventRecord(P->ev_lock_small, P->s_small));
+    CK(cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0));          // lstm_byte_kernel reads it too
+  }
+  small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, ppmd, 0, dbit);      // concurrent with the mixer / LSTM update
+  mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay, dbit);
+  if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd, dbit); P->launches++; }
+  // FXCM is perceived last and sees the LSTM's read-out of the next bit (predictor.cpp:462-466); PAQ8 needs the bit only
+  if (P->d_fx) { fxcm_launch_bit(P->d_st, P->d_fx, bit, 0, P->d_ext_bit, P->s_mix, dbit); P->launches++; }
+  if (P->d_p8) {
+    paq8_launch_bit(P->d_p8, bit, P->d_ext_bit, P->s_p8, dbit);
+    P->launches++;
+    CK(cudaEventRecord(P->ev_lock_p8, P->s_p8));
+  }
+  CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
+  P->launches += 2;
+  CK(cudaGetLastError());
+  P->bits_done++;
+  return CMIXB200_OK;
+}
+
 int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   CK(cudaSetDevice(P->device));
   bit = bit ? 1 : 0;
   const bool byte_done = P->bit_context >= 128;
   const u32 full = (P->bit_context * 2 + bit) & 255;
-  const float* ppmd = byte_done ? P->d_ppmd_byte : nullptr;
-  float decay = 0.9 / pow(0.0000001 * (unsigned long long)P->bits_done + 0.8, 0.8);
-  if (byte_done && !P->ppmd_byte_valid) {
-    // no replayed distribution for this byte: the resident PPMD model is updated and emits it (ppmd.cpp:1328-1338)
-    ppmd_byte_kernel<<<1, 32, sizeof(PpmdWarpShared), P->s_small>>>(P->d_st, full, P->d_ppmd_byte);
-    P->launches++;
-    CK(cudaEventRecord(P->ev_lock_small, P->s_small));
-    CK(cudaStreamWaitEvent(P->s_mix, P->ev_lock_small, 0));          // lstm_byte_kernel reads it too
-  }
-  // queued, not awaited: the host goes back to the arithmetic coder while the update runs; the next
-  // Predict() (same CUDA stream) is ordered behind it
-  small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, bit, ppmd, 0);      // concurrent with the mixer / LSTM update
-  mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, bit, decay);
-  if (byte_done) { lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, full, ppmd); P->launches++; }
-  // FXCM is perceived last and sees the LSTM's read-out of the next bit (predictor.cpp:462-466)
-  if (P->d_fx) { fxcm_launch_bit(P->d_st, P->d_fx, bit, 0, P->d_ext_bit, P->s_mix); P->launches++; }
-  if (P->d_p8) { paq8_launch_bit(P->d_p8, bit, P->d_ext_bit, P->s_mix); P->launches++; }
-  CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));
-  P->launches += 2;
-  CK(cudaGetLastError());
-  P->bits_done++;
+  // the previous Predict() waited for s_mix, so the row kernel that read d_ext_bit is done before PAQ8 rewrites its slots
+  TRY(LaunchPerceive(P, bit, full, byte_done, nullptr));
   P->bit_context = byte_done ? 1 : P->bit_context * 2 + bit;
   if (byte_done) P->ppmd_byte_valid = false;
   return CMIXB200_OK;
+}
+
+// Decoder::Decode for n_bytes on the device: predict kernels, one arithmetic-decoder step, perceive kernels,
+// bit after bit without a host round trip; the host only queues launches and waits once at the end.
+int cmixb200_decode_bytes(cmixb200_predictor* P, const uint8_t* archive, size_t n_archive, uint8_t* out, size_t n_bytes) {
+  CK(cudaSetDevice(P->device));
+  if (!archive || !out) { g_last_error = "decode_bytes: null argument"; return CMIXB200_ERR_ARG; }
+  if (P->bit_context != 1) { g_last_error = "decode_bytes: the stream must stand on a byte boundary"; return CMIXB200_ERR_ARG; }
+  if ((P->replay_mask & (CMIXB200_REPLAY_FXCM | CMIXB200_REPLAY_PAQ8)) != 0) { g_last_error = "decode_bytes needs every model group resident"; return CMIXB200_ERR_ARG; }
+  if (n_bytes == 0) return CMIXB200_OK;
+  u8 *d_arch = nullptr, *d_out = nullptr;
+  DecodeState* d_ds = nullptr;
+  int r = CMIXB200_OK;
+  auto fail = [&](const char* what) { g_last_error = std::string("decode_bytes: ") + what; r = CMIXB200_ERR_CUDA; };
+  if (cudaMalloc(&d_arch, n_archive ? n_archive : 1) != cudaSuccess || cudaMalloc(&d_out, n_bytes) != cudaSuccess || cudaMalloc(&d_ds, sizeof(DecodeState)) != cudaSuccess) fail("out of device memory");
+  if (r == CMIXB200_OK) {
+    DecodeState h;
+    memset(&h, 0, sizeof h);
+    h.n_arch = n_archive; h.arch = d_arch; h.out = d_out;
+    if (cudaMemcpyAsync(d_arch, archive, n_archive, cudaMemcpyHostToDevice, P->s_mix) != cudaSuccess ||
+        cudaMemcpyAsync(d_ds, &h, sizeof h, cudaMemcpyHostToDevice, P->s_mix) != cudaSuccess) fail("upload failed");
+    else decode_begin_kernel<<<1, 1, 0, P->s_mix>>>(d_ds);
+  }
+  const u32* dbit = reinterpret_cast<const u32*>(d_ds);
+  for (size_t t = 0; r == CMIXB200_OK && t < n_bytes * 8; ++t) {
+    r = LaunchPredict(P);
+    if (r != CMIXB200_OK) break;
+    decode_step_kernel<<<1, 1, 0, P->s_mix>>>(P->d_st, d_ds);
+    P->launches++;
+    r = LaunchPerceive(P, 0, 0, (t & 7) == 7, dbit);
+    if ((t & 7) == 7) P->ppmd_byte_valid = false;
+    if ((t & 1023) == 1023 && r == CMIXB200_OK) {      // bound the launch queue and surface device errors early
+      const cudaError_t ce = cudaStreamSynchronize(P->s_mix);
+      if (ce != cudaSuccess) fail(cudaGetErrorString(ce));
+    }
+  }
+  if (r == CMIXB200_OK) {
+    cudaError_t ce = cudaStreamSynchronize(P->s_mix);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(P->s_small);
+    if (ce == cudaSuccess && P->s_p8) ce = cudaStreamSynchronize(P->s_p8);
+    if (ce != cudaSuccess) fail(cudaGetErrorString(ce));
+    else if (cudaMemcpy(out, d_out, n_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) fail("download failed");
+  }
+  if (r == CMIXB200_OK) r = CheckPaq8(P);
+  if (r == CMIXB200_OK && P->d_ppmd_model) {
+    uint32_t err = 0;
+    if (cudaMemcpy(&err, (const char*)P->d_ppmd_model + offsetof(PpmdModel, error), 4, cudaMemcpyDeviceToHost) == cudaSuccess && err) {
+      g_last_error = "PPMD arena exhausted: raise CMIXB200_PPMD_MB (the reference would cut its model off here)"; r = CMIXB200_ERR_CAPACITY;
+    }
+  }
+  cudaFree(d_arch); cudaFree(d_out); cudaFree(d_ds);
+  return r;
 }
 
 int cmixb200_pretrain(cmixb200_predictor* P, int bit) {

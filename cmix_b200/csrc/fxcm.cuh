@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(FX_THREADS, 1) fxcm_kernel(const ChunkArgs* __
 // Lock-step: one bit per launch (the decoder's order), queued behind the mixer / LSTM update of the same bit. Lane 0 first
 // takes the LSTM's read-out of the NEXT bit (ByteMixer::Predict + Discretize, predictor.cpp:462-465); the codes for the next
 // Predict() land in ext_bit[0..430].
-__global__ void __launch_bounds__(FX_THREADS, 1) fxcm_bit_kernel(StreamState* st, fx::State* g, int y, int pretrain, u16* ext_bit) {
+__global__ void __launch_bounds__(FX_THREADS, 1) fxcm_bit_kernel(StreamState* st, fx::State* g, int y, int pretrain, u16* ext_bit, const u32* dbit) {
+  if (dbit) y = (int)dbit[0];
   extern __shared__ __align__(16) unsigned char fx_raw[];
   FxShared& sh = *reinterpret_cast<FxShared*>(fx_raw);
   const int tid = threadIdx.x;

@@ -694,7 +694,8 @@ __global__ void __launch_bounds__(64, 1) lock_predict_inputs_kernel(StreamState*
   small_predict(st->small, T, sh, st->small_x, st->sel, tid);
 }
 __global__ void __cluster_dims__(LSTM_CTAS, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
-lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd) {
+lstm_byte_kernel(StreamState* st, u32 byte, const float* ppmd, const u32* dbit = nullptr) {
+  if (dbit) byte = dbit[1];
   cgl::cluster_group cluster = cgl::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LstmShared& sh = *reinterpret_cast<LstmShared*>(smem_raw);

@@ -500,7 +500,8 @@ mix_predict_final_kernel(StreamState* st, Tables T) {
 // layers 1-2, the SSE update and the step counter; CTA 27 the LSTM read-out's bit update
 // (ByteModel::Perceive, byte-model.cpp:17-30).
 __global__ void __launch_bounds__(MIX_THREADS, 1)
-mix_perceive_kernel(StreamState* st, int bit, float decay_base) {
+mix_perceive_kernel(StreamState* st, int bit, float decay_base, const u32* dbit = nullptr) {
+  if (dbit) bit = (int)dbit[0];          // decode loop: the bit comes from decode_step_kernel, not from the host
   __shared__ float upd[N_L1 + 2];
   __shared__ u32 shrink[N_L1 + 2];
   const int tid = threadIdx.x, blk = blockIdx.x;

@@ -314,6 +314,7 @@ __device__ __forceinline__ void p8_advance_rnd(P8Shared& sh, int lane) {
   p8::Rnd& r = sh.S.rnd;
   const int total = p8_flags_in(sh.flag_mask, 0, P8_CM_LANES);
   const int i0 = r.i;
+  __syncwarp();
   for (int s0 = 0; s0 < total; s0 += 24) {
     const int n = min(24, total - s0);
     const int idx = i0 + 1 + s0 + lane;
@@ -507,7 +508,7 @@ __device__ __forceinline__ void p8_sgd(P8Shared& sh, int t) {
 }
 
 // One bit: PAQ8::Perceive(y). All P8_THREADS lanes call it: warps 0-11 evaluate the models, warps 12-15 train the mixer beside them.
-__device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit position after this bit, (S.bpos + 1) & 7
+__device__ void p8_bit(P8Shared& sh, int y, int nb, int tid, bool fresh = false) {   // nb: the bit position after this bit, (S.bpos + 1) & 7; fresh: shared memory holds nothing from the previous bit
   using namespace p8;
   State& S = sh.S;
   const p8::Tables& T = *S.T;
@@ -529,7 +530,7 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid) {   // nb: the bit 
   if (tid >= 96 && tid < 96 + N_SETS) sh.sgd_err[tid - 96] = ((y << 12) - S.m.pr[tid - 96]) * 7;
   if (tid >= 128 && tid < 128 + N_IN / 8) reinterpret_cast<uint4*>(sh.tx_old)[tid - 128] = reinterpret_cast<const uint4*>(S.m.tx)[tid - 128];
   if (tid >= P8_CM2_TID0 && tid < P8_CM2_TID0 + P8_N_CM2) cm2_begin(p8_cm2(S, tid - P8_CM2_TID0), y, nb);
-  if (warp == P8_WARPS - 1 && nb <= 1) {      // mixer-input offsets of the units (they change on the first two bits of a byte only)
+  if (warp == P8_WARPS - 1 && (nb <= 1 || fresh)) {      // mixer-input offsets of the units (they change on the first two bits of a byte only)
     const unsigned full = 0xffffffffu;
     const int a = p8_unit_count(S, lane, nb == 0);
     const int b = lane + 32 < P8_N_UNITS ? p8_unit_count(S, lane + 32, nb == 0) : 0;
@@ -778,13 +779,14 @@ __global__ void __launch_bounds__(P8_THREADS, 1) paq8_kernel(const ChunkArgs* __
 }
 
 // Lock-step: one bit per launch; the codes for the next Predict() land in ext_bit[431..2021].
-__global__ void __launch_bounds__(P8_THREADS, 1) paq8_bit_kernel(p8::State* g, int y, u16* ext_bit) {
+__global__ void __launch_bounds__(P8_THREADS, 1) paq8_bit_kernel(p8::State* g, int y, u16* ext_bit, const u32* dbit) {
+  if (dbit) y = (int)dbit[0];
   extern __shared__ __align__(16) unsigned char p8_raw[];
   P8Shared& sh = *reinterpret_cast<P8Shared*>(p8_raw);
   const int tid = threadIdx.x;
   const int nb = (g->bpos + 1) & 7;       // read from HBM: the shared copy is being updated by lane 0 inside p8_bit
   const p8::Tables* gT = p8_enter(sh, g, tid);
-  p8_bit(sh, y, nb, tid);
+  p8_bit(sh, y, nb, tid, true);
   if (ext_bit) for (int k = tid; k < p8::N_OUT; k += P8_THREADS) ext_bit[431 + k] = sh.S.codes[k];
   p8_leave(sh, g, gT, tid);
 }

@@ -12,8 +12,8 @@ cudaError_t paq8_configure() {
 void paq8_launch_chunk(const ChunkArgs* d_args, int n_streams, cudaStream_t s) {
   paq8_kernel<<<n_streams, P8_THREADS, sizeof(P8Shared), s>>>(d_args);
 }
-void paq8_launch_bit(p8::State* g, int y, u16* ext_bit, cudaStream_t s) {
-  paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), s>>>(g, y, ext_bit);
+void paq8_launch_bit(p8::State* g, int y, u16* ext_bit, cudaStream_t s, const u32* dbit) {
+  paq8_bit_kernel<<<1, P8_THREADS, sizeof(P8Shared), s>>>(g, y, ext_bit, dbit);
 }
 
 }  // namespace cmixb200

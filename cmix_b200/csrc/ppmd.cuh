@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(PPMD_WARPS * 32, 1) ppmd_kernel(const ChunkArg
 }
 
 // Lock-step: one byte.
-__global__ void __launch_bounds__(32, 1) ppmd_byte_kernel(StreamState* st, u32 byte, float* out) {
+__global__ void __launch_bounds__(32, 1) ppmd_byte_kernel(StreamState* st, u32 byte, float* out, const u32* dbit = nullptr) {
+  if (dbit) byte = dbit[1];
   extern __shared__ __align__(16) unsigned char ppmd_raw[];
   PpmdWarpShared& sh = *reinterpret_cast<PpmdWarpShared*>(ppmd_raw);
   const int lane = threadIdx.x;

@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(64, 1) small_predict_kernel(StreamState* st, T
   __syncthreads();
   small_predict(st->small, T, sh, st->small_x, st->sel, tid);
 }
-__global__ void __launch_bounds__(64, 1) small_perceive_kernel(StreamState* st, int bit, const float* ppmd_next, int pretrain) {
+__global__ void __launch_bounds__(64, 1) small_perceive_kernel(StreamState* st, int bit, const float* ppmd_next, int pretrain, const u32* dbit = nullptr) {
+  if (dbit) bit = (int)dbit[0];
   __shared__ SmallShared sh;
   SmallState& s = st->small;
   const int tid = threadIdx.x;

@@ -169,6 +169,15 @@ struct CoderState {
   u8* out;
 };
 
+// Decoder::Decode on the device (coder.cuh decode_step_kernel): the arithmetic decoder's registers, the archive and what the
+// lock-step kernels of a decode loop read instead of host arguments (bit / full, in this order: they are passed as one pointer).
+struct DecodeState {
+  u32 bit, full;                // the bit just decoded; the byte it completed (valid on the 8th bit of a byte)
+  u32 x1, x2, x, ctx;           // Decoder::x1_, x2_, x_ (decoder.cpp:3-8); bits of the current byte with a leading 1
+  u64 pos, n_arch, t;           // next archive byte, archive length, bits decoded
+  const u8* arch; u8* out;
+};
+
 struct ChunkArgs {
   StreamState* st;
   const u8* bytes;              // [n_bytes] the coded stream

@@ -84,6 +84,13 @@ int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t
  * archive; overflow is reported by finish, never written past. */
 int cmixb200_coder_begin(cmixb200_predictor*, size_t capacity_bytes);
 int cmixb200_coder_finish(cmixb200_predictor*, uint8_t* out, size_t cap, size_t* n_out);
+
+/* Decompress direction on the device: replaces the loop of Decompress() (reference src/runner.cpp:121-137,
+ * i.e. Decoder::Decoder + n_bytes*8 calls of Decoder::Decode, src/coder/decoder.cpp:3-39). `archive` is the arithmetic-coded body
+ * (what follows the header runner.cpp:62-86 reads), `out` receives n_bytes decoded bytes. Per bit the library queues the predict
+ * kernels, one decoder step and the perceive kernels; the bit never visits the host. Needs every model group resident and a stream
+ * standing on a byte boundary. */
+int cmixb200_decode_bytes(cmixb200_predictor*, const uint8_t* archive, size_t n_archive, uint8_t* out, size_t n_bytes);
 /* preprocessor::Pretrain's loop (preprocessor.cpp:37-69) over a byte buffer (HOST). */
 int cmixb200_pretrain_bytes(cmixb200_predictor*, const uint8_t* bytes, size_t n_bytes);
 
