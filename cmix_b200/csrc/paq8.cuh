@@ -68,7 +68,7 @@ struct P8Shared {
   int flag_base[P8_N_CM];      // index of a map's first draw in draws[]
   u32 draws[P8_CM_LANES + 6];
   u32 rnd_prev[64]; int rnd_prev_i;   // the generator as the bit found it: flagged contexts compute their own draw from it
-  int any_clash;
+  int any_clash, text_pending;
   union {
     unsigned long long seen[P8_SEEN];   // open-addressing set of (map, bucket) pairs touched this bit
     struct { double ch[3][32 * 33]; double pb[3][32]; } ols;   // Cholesky factor rows (padded) and a product buffer; byte boundaries only
@@ -570,17 +570,18 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid, bool fresh = false)
       {
         P8_M0;
         if (warp < 3) p8_ols_byte_warp(sh, warp, lane);
-        else if (warp == 8) {       // the text model: state on one lane, its 33 contexts side by side
-          if (lane == 0) text_update(S);
+        else if (warp == 8) {       // the text model: state on one lane (the stemmers of a completed word follow below)
+          if (lane == 0) sh.text_pending = text_update_a(S);
+        } else if (warp == 5) {     // the word model: state on one lane, its 57 contexts side by side
+          if (lane == 0) word_update(S);
           __syncwarp();
-          const int n = text_contexts(S, CtxSel{lane, 32});
+          const int n = word_contexts(S, CtxSel{lane, 32});
           __syncwarp();
-          if (lane == 0) S.text.map.index = n;
+          if (lane == 0) { S.word.cm.cn = n; word_finish(S); }
         } else if (lane == 0) {
           switch (warp) {
             case 3: ordern_byte(S); break;
             case 4: distance_byte(S); record1_byte(S); break;
-            case 5: word_byte(S); break;
             case 6: nest_byte(S); indirect_byte(S); break;
             case 7: xml_byte(S); break;
             case 9: exe_byte(S); break;
@@ -594,6 +595,25 @@ __device__ void p8_bit(P8Shared& sh, int y, int nb, int tid, bool fresh = false)
         if (lane == 0) P8_M(24 + warp);
       }
       p8_sync_maps();
+      if (sh.text_pending) {      // a word ended: its three stemmers on three warps, then the rest of the text model's byte
+        const int split = S.text.stem_split;
+        if (lane == 0 && (warp == 8 || warp == 10 || warp == 11)) {
+          const int i = warp == 8 ? LANG_EN : (warp == 10 ? LANG_FR : LANG_DE);
+          if (i >= split) text_stem(S, i);
+        }
+        p8_sync_maps();
+        if (tid == 8 * 32) {
+          text_stem_mid(S);
+          for (int i = split - 1; i > LANG_UNKNOWN; --i) text_stem(S, i);
+          text_update_b(S);
+        }
+        p8_sync_maps();
+      }
+      if (warp == 8) {            // the text model's 33 contexts side by side
+        const int n = text_contexts(S, CtxSel{lane, 32});
+        __syncwarp();
+        if (lane == 0) S.text.map.index = n;
+      }
       P8_T(2);
       for (int k = tid; k < P8_SEEN; k += P8_MAP_THREADS) sh.u.seen[k] = 0ull;   // the OLS warps used this memory
       p8_sync_maps();

@@ -397,6 +397,12 @@ P8_HD inline void cm2_put(Cm2& m, int k, u64 ctx) {
   m.cxt[k] = finalize64(ctx, m.hashbits);
   m.chk[k] = (u16)(checksum64(ctx, m.hashbits, 16) & 0xffff);
 }
+P8_HD inline void cm_put(Cm& m, int k, u64 cx) {
+  cx = hash(cx, (u64)k);
+  m.cxt[k] = finalize64(cx, m.hashbits);
+  m.chk[k] = (u16)(checksum64(cx, m.hashbits, 16) & 0xffff);
+}
+#define P8_CM_SET(sel, m, k, expr) do { if (ctx_mine(sel, k)) cm_put(m, k, (expr)); ++k; } while (0)
 #define P8_CM2_SET(sel, m, k, expr) do { if (ctx_mine(sel, k)) cm2_put(m, k, (expr)); ++k; } while (0)
 // ---- ContextMap2::mix (:1294-1358) including Update (:1204-1260), cut into prologue / per-context step / epilogue
 P8_HD inline void cm2_begin(Cm2& m, int y, int bpos) {

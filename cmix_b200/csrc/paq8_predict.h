@@ -32,6 +32,7 @@ struct WordM {   // wordModel (:3872-4105)
   u64 word0, word1, word2, word3, word4, word5, xword0, xword1, xword2, cword0, ccword, number0, number1;
   u32 wrdhsh, text0, data0, type0, last_letter, first_letter, last_upper, last_digit, word_gap, mask, mask2;
   int nl1, nl, w, cword, pword, stem_index;
+  int above, f_pending;  // handed from word_update to word_contexts / word_finish
   int* wpos;             // [0x10000]
   Word stem[4];
   Cm cm;
@@ -84,6 +85,7 @@ struct TextM {   // TextModel (:3070-3519)
   u32 masks[5], word_length[2];
   int utf8_remaining;
   u8 first_letter, first_char, expected_digit, prev_punct;
+  u8 stem_ok[3], stem_split;   // verdicts of the three stemmers; the language list whose current word IS cWord (0: none)
   Word topic;
   u64 parse_ctx;
 };
@@ -609,10 +611,12 @@ P8_HD inline void record1_bit(State& S, Out& o, Rnd& rnd) {
 }
 
 // ---------------------------------------------------------------- word model (:3872-4105)
-P8_HD inline void word_byte(State& S) {
+// wordModel at a byte boundary (:3873-4104) in three pieces: word_update changes the state (one lane), word_contexts is the pure
+// list of the 57 contexts (a warp can share it: CtxSel), word_finish applies the sentence-end shift the reference does between
+// contexts 41 and 42 (the contexts after it use the shifted words, computed locally).
+P8_HD inline void word_update(State& S) {
   const Tables& T = *S.T;
   WordM& M = S.word;
-  Cm& cm = M.cm;
   const u32 c4 = S.c4;
   int c = (int)(c4 & 255);
   const int pC = (u8)(c4 >> 8);
@@ -700,89 +704,114 @@ P8_HD inline void word_byte(State& S) {
   const int above = bufa(S, (u32)(M.nl1 + (int)S.col));
   if (S.col <= 2) S.frstchar = (S.col == 2 ? (u32)imin(c, 96) : 0);
   if (S.frstchar == '[' && c == 32) { if (buf(S, 3) == ']' || buf(S, 4) == ']') { S.frstchar = 96; M.xword0 = 0; } }
+  {
+    int fl = 0;
+    const int cc = (int)(c4 & 0xff);
+    if (cc != 0) {
+      if (is_alpha(cc)) fl = 1;
+      else if (is_punct(cc)) fl = 2;
+      else if (is_space(cc)) fl = 3;
+      else if (cc == 0xff) fl = 4;
+      else if (cc < 16) fl = 5;
+      else if (cc < 64) fl = 6;
+      else fl = 7;
+    }
+    M.mask = (M.mask << 3) | (u32)fl;
+  }
+  M.above = above;
+  M.f_pending = f;
+}
+P8_HD inline int word_contexts(State& S, const CtxSel sel) {
+  const Tables& T = *S.T;
+  WordM& M = S.word;
+  Cm& cm = M.cm;
+  const u32 c4 = S.c4;
+  int c = (int)(c4 & 255);
+  if (c >= 'A' && c <= 'Z') c += 'a' - 'A';
+  const int above = M.above, f = M.f_pending;
+  // the words as the contexts after the sentence-end shift see them (word_finish applies it to the state)
+  const u64 nword1 = f ? (u64)'.' : M.word1, nword2 = f ? M.word1 : M.word2;
+  int n = cm.cn;
   const u32 col = S.col, frstchar = S.frstchar, spaces = S.spaces, spafdo = S.spafdo, wordlen = S.wordlen, wordlen1 = S.wordlen1;
-  cm_set(cm, hash(513, spafdo, spaces, M.ccword));
-  cm_set(cm, hash(514, frstchar, sx(c)));
-  cm_set(cm, hash(515, col, frstchar, (u64)((M.last_upper < col) * 4 + (M.mask2 & 3))));
-  cm_set(cm, hash(516, spaces, (u64)(S.words & 255)));
-  cm_set(cm, spaces & 0x7fff);
-  cm_set(cm, spaces & 0xff);
-  cm_set(cm, hash(257, M.number0, M.word1, M.word_gap));
-  cm_set(cm, hash(258, M.number1, sx(c), M.ccword));
-  cm_set(cm, hash(259, M.number0, M.number1, M.word_gap));
-  cm_set(cm, hash(260, M.word0, M.number1, (u64)(M.last_digit < M.word_gap + wordlen)));
-  cm_set(cm, hash(274, M.number0, M.cword0));
-  cm_set(cm, hash(518, wordlen1, col));
-  cm_set(cm, hash(519, sx(c), (u64)(S.spacecount / 2), M.word_gap));
+  P8_CM_SET(sel, cm, n, hash(513, spafdo, spaces, M.ccword));
+  P8_CM_SET(sel, cm, n, hash(514, frstchar, sx(c)));
+  P8_CM_SET(sel, cm, n, hash(515, col, frstchar, (u64)((M.last_upper < col) * 4 + (M.mask2 & 3))));
+  P8_CM_SET(sel, cm, n, hash(516, spaces, (u64)(S.words & 255)));
+  P8_CM_SET(sel, cm, n, spaces & 0x7fff);
+  P8_CM_SET(sel, cm, n, spaces & 0xff);
+  P8_CM_SET(sel, cm, n, hash(257, M.number0, M.word1, M.word_gap));
+  P8_CM_SET(sel, cm, n, hash(258, M.number1, sx(c), M.ccword));
+  P8_CM_SET(sel, cm, n, hash(259, M.number0, M.number1, M.word_gap));
+  P8_CM_SET(sel, cm, n, hash(260, M.word0, M.number1, (u64)(M.last_digit < M.word_gap + wordlen)));
+  P8_CM_SET(sel, cm, n, hash(274, M.number0, M.cword0));
+  P8_CM_SET(sel, cm, n, hash(518, wordlen1, col));
+  P8_CM_SET(sel, cm, n, hash(519, sx(c), (u64)(S.spacecount / 2), M.word_gap));
   u32 h = S.wordcount * 64 + S.spacecount;
-  cm_set(cm, hash(520, sx(c), h, M.ccword));
-  cm_set(cm, hash(517, frstchar, h, M.last_letter));
-  cm_set(cm, hash(M.data0, M.word1, M.number1, (u64)(M.type0 & 0xFFF)));
-  cm_set(cm, hash(521, h, spafdo));
+  P8_CM_SET(sel, cm, n, hash(520, sx(c), h, M.ccword));
+  P8_CM_SET(sel, cm, n, hash(517, frstchar, h, M.last_letter));
+  P8_CM_SET(sel, cm, n, hash(M.data0, M.word1, M.number1, (u64)(M.type0 & 0xFFF)));
+  P8_CM_SET(sel, cm, n, hash(521, h, spafdo));
   const u32 d = c4 & 0xf0ff;
-  cm_set(cm, hash(522, d, frstchar, M.ccword));
+  P8_CM_SET(sel, cm, n, hash(522, d, frstchar, M.ccword));
   h = (u32)(M.word0 * 271);
   h = h + (u32)buf(S, 1);
-  cm_set(cm, hash(262, h, 0));
-  cm_set(cm, hash(M.number0 * 271 + (u64)buf(S, 1), 0));
-  cm_set(cm, hash(263, M.word0, 0));
-  if (M.wrdhsh) cm_set(cm, hash(M.wrdhsh, (u64)buf(S, M.wpos[M.word1 & 0xffff]))); else cm_set(cm, 0);
-  cm_set(cm, hash(264, h, M.word1));
-  cm_set(cm, hash(265, M.word0, M.word1));
-  cm_set(cm, hash(266, h, M.word1, M.word2, (u64)(M.last_upper < wordlen)));
-  cm_set(cm, hash(267, (u64)(M.text0 & 0xffffff), 0));
-  cm_set(cm, M.text0 & 0xfffff);
-  cm_set(cm, hash(269, M.word0, M.xword0));
-  cm_set(cm, hash(270, h, M.xword1));
-  cm_set(cm, hash(271, h, M.xword2));
-  cm_set(cm, hash(272, frstchar, M.xword2));
-  cm_set(cm, hash(273, M.word0, M.cword0));
-  cm_set(cm, hash(275, h, M.word2));
-  cm_set(cm, hash(276, h, M.word3));
-  cm_set(cm, hash(277, h, M.word4));
-  cm_set(cm, hash(278, h, M.word5));
-  cm_set(cm, hash(279, h, M.word1, M.word3));
-  cm_set(cm, hash(280, h, M.word2, M.word3));
-  cm_set(cm, (u64)(buf(S, 1) | buf(S, 3) << 8 | buf(S, 5) << 16));
-  cm_set(cm, (u64)(buf(S, 2) | buf(S, 4) << 8 | buf(S, 6) << 16));
-  cm_set(cm, (u64)(buf(S, 1) | buf(S, 4) << 8 | buf(S, 7) << 16));
-  if (f) { M.word5 = M.word4; M.word4 = M.word3; M.word3 = M.word2; M.word2 = M.word1; M.word1 = '.'; }
+  P8_CM_SET(sel, cm, n, hash(262, h, 0));
+  P8_CM_SET(sel, cm, n, hash(M.number0 * 271 + (u64)buf(S, 1), 0));
+  P8_CM_SET(sel, cm, n, hash(263, M.word0, 0));
+  if (M.wrdhsh) P8_CM_SET(sel, cm, n, hash(M.wrdhsh, (u64)buf(S, M.wpos[M.word1 & 0xffff]))); else P8_CM_SET(sel, cm, n, 0);
+  P8_CM_SET(sel, cm, n, hash(264, h, M.word1));
+  P8_CM_SET(sel, cm, n, hash(265, M.word0, M.word1));
+  P8_CM_SET(sel, cm, n, hash(266, h, M.word1, M.word2, (u64)(M.last_upper < wordlen)));
+  P8_CM_SET(sel, cm, n, hash(267, (u64)(M.text0 & 0xffffff), 0));
+  P8_CM_SET(sel, cm, n, M.text0 & 0xfffff);
+  P8_CM_SET(sel, cm, n, hash(269, M.word0, M.xword0));
+  P8_CM_SET(sel, cm, n, hash(270, h, M.xword1));
+  P8_CM_SET(sel, cm, n, hash(271, h, M.xword2));
+  P8_CM_SET(sel, cm, n, hash(272, frstchar, M.xword2));
+  P8_CM_SET(sel, cm, n, hash(273, M.word0, M.cword0));
+  P8_CM_SET(sel, cm, n, hash(275, h, M.word2));
+  P8_CM_SET(sel, cm, n, hash(276, h, M.word3));
+  P8_CM_SET(sel, cm, n, hash(277, h, M.word4));
+  P8_CM_SET(sel, cm, n, hash(278, h, M.word5));
+  P8_CM_SET(sel, cm, n, hash(279, h, M.word1, M.word3));
+  P8_CM_SET(sel, cm, n, hash(280, h, M.word2, M.word3));
+  P8_CM_SET(sel, cm, n, (u64)(buf(S, 1) | buf(S, 3) << 8 | buf(S, 5) << 16));
+  P8_CM_SET(sel, cm, n, (u64)(buf(S, 2) | buf(S, 4) << 8 | buf(S, 6) << 16));
+  P8_CM_SET(sel, cm, n, (u64)(buf(S, 1) | buf(S, 4) << 8 | buf(S, 7) << 16));
   if (col < 255u) {
-    cm_set(cm, hash(523, col, (u64)buf(S, 1), sx(above)));
-    cm_set(cm, hash(524, (u64)buf(S, 1), sx(above)));
-    cm_set(cm, hash(525, col, (u64)buf(S, 1)));
-    cm_set(cm, hash(526, col, (u64)(c == 32)));
-  } else { cm_set(cm, 0); cm_set(cm, 0); cm_set(cm, 0); cm_set(cm, 0); }
-  if (wordlen) cm_set(cm, hash(281, M.word0, sx(llog(T, (u32)(S.blpos - M.wpos[M.word1 & 0xffff])) >> 4)));
-  else cm_set(cm, 0);
-  cm_set(cm, hash(282, (u64)buf(S, 1), sx(llog(T, (u32)(S.blpos - M.wpos[M.word1 & 0xffff])) >> 2)));
-  cm_set(cm, hash(283, (u64)buf(S, 1), M.word0, sx(llog(T, (u32)(S.blpos - M.wpos[M.word2 & 0xffff])) >> 2)));
-  int fl = 0;
-  const int cc = (int)(c4 & 0xff);
-  if (cc != 0) {
-    if (is_alpha(cc)) fl = 1;
-    else if (is_punct(cc)) fl = 2;
-    else if (is_space(cc)) fl = 3;
-    else if (cc == 0xff) fl = 4;
-    else if (cc < 16) fl = 5;
-    else if (cc < 64) fl = 6;
-    else fl = 7;
-  }
-  M.mask = (M.mask << 3) | (u32)fl;
-  cm_set(cm, hash(528, M.mask, 0));
-  cm_set(cm, hash(529, M.mask, (u64)buf(S, 1)));
-  cm_set(cm, hash(530, (u64)(M.mask & 0xff), col));
-  cm_set(cm, hash(531, M.mask, (u64)buf(S, 2), (u64)buf(S, 3)));
-  cm_set(cm, hash(532, (u64)(M.mask & 0x1ff), (u64)(S.f4 & 0x00fff0)));
-  cm_set(cm, hash(h, sx(llog(T, M.word_gap)), (u64)(M.mask & 0x1FF),
+    P8_CM_SET(sel, cm, n, hash(523, col, (u64)buf(S, 1), sx(above)));
+    P8_CM_SET(sel, cm, n, hash(524, (u64)buf(S, 1), sx(above)));
+    P8_CM_SET(sel, cm, n, hash(525, col, (u64)buf(S, 1)));
+    P8_CM_SET(sel, cm, n, hash(526, col, (u64)(c == 32)));
+  } else { P8_CM_SET(sel, cm, n, 0); P8_CM_SET(sel, cm, n, 0); P8_CM_SET(sel, cm, n, 0); P8_CM_SET(sel, cm, n, 0); }
+  if (wordlen) P8_CM_SET(sel, cm, n, hash(281, M.word0, sx(llog(T, (u32)(S.blpos - M.wpos[nword1 & 0xffff])) >> 4)));
+  else P8_CM_SET(sel, cm, n, 0);
+  P8_CM_SET(sel, cm, n, hash(282, (u64)buf(S, 1), sx(llog(T, (u32)(S.blpos - M.wpos[nword1 & 0xffff])) >> 2)));
+  P8_CM_SET(sel, cm, n, hash(283, (u64)buf(S, 1), M.word0, sx(llog(T, (u32)(S.blpos - M.wpos[nword2 & 0xffff])) >> 2)));
+  P8_CM_SET(sel, cm, n, hash(528, M.mask, 0));
+  P8_CM_SET(sel, cm, n, hash(529, M.mask, (u64)buf(S, 1)));
+  P8_CM_SET(sel, cm, n, hash(530, (u64)(M.mask & 0xff), col));
+  P8_CM_SET(sel, cm, n, hash(531, M.mask, (u64)buf(S, 2), (u64)buf(S, 3)));
+  P8_CM_SET(sel, cm, n, hash(532, (u64)(M.mask & 0x1ff), (u64)(S.f4 & 0x00fff0)));
+  P8_CM_SET(sel, cm, n, hash(h, sx(llog(T, M.word_gap)), (u64)(M.mask & 0x1FF),
                   (u64)(((wordlen1 > 3) << 6) | ((wordlen > 0) << 5) | ((spafdo == wordlen + 2) << 4) | ((spafdo == wordlen + wordlen1 + 3) << 3) |
                         ((spafdo >= M.last_letter + wordlen1 + M.word_gap) << 2) | ((M.last_upper < M.last_letter + wordlen1) << 1) |
                         (M.last_upper < wordlen + wordlen1 + M.word_gap)),
                   (u64)(M.type0 & 0xFFF)));
-  if (wordlen1) cm_set(cm, hash(col, wordlen1, sx(above & 0x5F), (u64)(c4 & 0x5F))); else cm_set(cm, 0);
-  if (M.wrdhsh) cm_set(cm, hash((u64)(M.mask2 & 0x3F), (u64)(M.wrdhsh & 0xFFF), (u64)((0x100 | M.first_letter) * (wordlen < 6)), (u64)((M.word_gap > 4) * 2 + (wordlen1 > 5))));
-  else cm_set(cm, 0);
-  if (M.last_letter < 16) cm_set(cm, hash(M.stem[M.pword].hash[2], h)); else cm_set(cm, 0);
+  if (wordlen1) P8_CM_SET(sel, cm, n, hash(col, wordlen1, sx(above & 0x5F), (u64)(c4 & 0x5F))); else P8_CM_SET(sel, cm, n, 0);
+  if (M.wrdhsh) P8_CM_SET(sel, cm, n, hash((u64)(M.mask2 & 0x3F), (u64)(M.wrdhsh & 0xFFF), (u64)((0x100 | M.first_letter) * (wordlen < 6)), (u64)((M.word_gap > 4) * 2 + (wordlen1 > 5))));
+  else P8_CM_SET(sel, cm, n, 0);
+  if (M.last_letter < 16) P8_CM_SET(sel, cm, n, hash(M.stem[M.pword].hash[2], h)); else P8_CM_SET(sel, cm, n, 0);
+  return n;
+}
+P8_HD inline void word_finish(State& S) {
+  WordM& M = S.word;
+  if (M.f_pending) { M.word5 = M.word4; M.word4 = M.word3; M.word3 = M.word2; M.word2 = M.word1; M.word1 = '.'; }
+}
+P8_HD inline void word_byte(State& S) {
+  word_update(S);
+  S.word.cm.cn = word_contexts(S, CtxSel{0, 1});
+  word_finish(S);
 }
 
 // ---------------------------------------------------------------- nest model (:4107-4181)

@@ -27,90 +27,11 @@ P8_HD inline void sentence_clear(Sentence& s) {
 }
 enum { TP_Unknown, TP_ReadingWord, TP_PossibleHyphenation, TP_WasAbbreviation, TP_AfterComma, TP_AfterQuote, TP_AfterAbbreviation, TP_ExpectDigit };
 
-P8_HD inline void text_update(State& S) {
-  const Tables& T = *S.T;
+// TextModel::Update (:3187-3375) in pieces so that the three stemmers of a completed word can run side by side on the device:
+// text_update_a does everything up to them (returns 1 when they are due), text_stem(lang) is one stemmer on its copy of the
+// word, text_update_b applies their verdicts and finishes the byte. text_update is the three in order.
+P8_HD inline void text_else_rest(State& S, u8 c, u8 pC) {
   TextM& M = S.text;
-  M.last_upper = umin(0xFF, M.last_upper + 1); M.mask_upper <<= 1;
-  M.last_letter = umin(0x1F, M.last_letter + 1);
-  M.last_digit = umin(0xFF, M.last_digit + 1);
-  M.last_punct = umin(0x3F, M.last_punct + 1);
-  M.last_newline++; M.prev_newline++; M.last_nest++;
-  M.space_count -= (M.spaces >> 31); M.spaces <<= 1;
-  M.masks[0] <<= 2; M.masks[1] <<= 2; M.masks[2] <<= 4; M.masks[3] <<= 3;
-  M.pstate = M.state;
-  u8 c = (u8)buf(S, 1), pC = (u8)lower(c);
-  const u8 g = (c < 0x80) ? T.ascii_group[c] : 31;
-  if (!((g <= 4) && g == (M.ascii_mask & 0x1f))) M.ascii_mask = ((M.ascii_mask << 5) | g) & ((1ull << 60) - 1);
-  M.masks[4] = (u32)(M.ascii_mask & ((1u << 30) - 1));
-  M.byte_pos[c] = (u32)S.pos;
-  if (c != pC) { c = pC; M.last_upper = 0; M.mask_upper |= 1; }
-  pC = (u8)buf(S, 2);
-  M.state = TP_Unknown;
-  M.parse_ctx = hash(sx(M.state), P8_PW.hash[1], c, (u64)((ilog2(M.last_newline) + 1) * (M.last_newline * 3 > M.prev_newline)), (u64)(M.masks[1] & 0xFC));
-  if ((c >= 'a' && c <= 'z') || c == '\'' || c == '-' || c > 0x7F) {
-    if (M.word_length[0] == 0) {
-      if (pC == 0x0A && ((M.last_letter == 3 && buf(S, 3) == '+') || (M.last_letter == 4 && buf(S, 3) == 0x0D && buf(S, 4) == '+'))) {
-        M.word_length[0] = M.word_length[1];
-        for (int i = LANG_UNKNOWN; i < LANG_COUNT; ++i) M.words_index[i]--;
-        // cWord = pWord, pWord = &Words[Lang.pId](1): as (lang, i) pairs relative to the decremented indices
-        M.cw_lang = M.pw_lang; M.cw_slot = M.pw_slot;
-        M.pw_lang = M.lang_pid; M.pw_slot = slot_of(M, M.lang_pid, 1);
-        P8_CW.clear();
-        for (u32 i = 0; i < M.word_length[0]; ++i) P8_CW.append(buf(S, (int)(M.word_length[0] - i + M.last_letter)));
-        M.word_length[1] = P8_PW.len();
-        tseg(M, 0).word_count--;
-        tsen(M, 0).word_count--;
-      } else { M.word_gap = M.last_letter; M.first_letter = c; }
-    }
-    M.last_letter = 0;
-    M.word_length[0]++;
-    M.masks[0] += (M.lang_id != LANG_UNKNOWN) ? 1 + (u32)lang_vowel(M.lang_id, c) : 1; M.masks[1]++; M.masks[3] += M.masks[0] & 3;
-    if (c == '\'') {
-      M.masks[2] += 12;
-      if (M.word_length[0] == 1) {
-        if (M.quote_length == 0 && pC == 0x20) M.quote_length = 1;
-        else if (M.quote_length > 0 && M.last_punct == 1) { M.quote_length = 0; M.state = TP_AfterQuote; M.parse_ctx = hash(sx(M.state), pC); }
-      }
-    }
-    P8_CW.append(c);
-    P8_CW.get_hashes();
-    M.state = TP_ReadingWord;
-    M.parse_ctx = hash(sx(M.state), P8_CW.hash[1]);
-  } else {
-    if (P8_CW.len() > 0) {
-      if (M.lang_id != LANG_UNKNOWN) word_copy(tw(M, LANG_UNKNOWN, 0), P8_CW);
-      for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i) {
-        M.lang_count[i - 1] -= (u32)(M.lang_mask[i - 1] >> 63); M.lang_mask[i - 1] <<= 1;
-        if (i != M.lang_id) word_copy(tw(M, i, 0), P8_CW);
-        Word& w = tw(M, i, 0);
-        const bool ok = i == LANG_EN ? StemEN::stem(w) : i == LANG_FR ? StemFR::stem(w) : StemDE::stem(w);
-        if (ok) { M.lang_count[i - 1]++; M.lang_mask[i - 1] |= 1; }
-      }
-      M.lang_id = LANG_UNKNOWN;
-      u32 best = 4;
-      for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i) {
-        if (M.lang_count[i - 1] >= best) { best = M.lang_count[i - 1] + (i == M.lang_pid); M.lang_id = i; }
-        M.words_index[i]++;
-      }
-      M.words_index[LANG_UNKNOWN]++;
-      M.lang_pid = M.lang_id;
-      M.pw_lang = M.cw_lang = M.lang_id; M.pw_slot = slot_of(M, M.lang_id, 1); M.cw_slot = slot_of(M, M.lang_id, 0);
-      P8_CW.clear();
-      M.word_pos[P8_PW.hash[1] & 0xffff] = (u32)S.pos;
-      Segment& seg = tseg(M, 0);
-      Sentence& sen = tsen(M, 0);
-      if (seg.word_count == 0) word_copy(seg.first_word, P8_PW);
-      seg.word_count++;
-      if (sen.word_count == 0) word_copy(sen.first_word, P8_PW);
-      sen.word_count++;
-      M.word_length[1] = M.word_length[0]; M.word_length[0] = 0;
-      M.quote_length += (M.quote_length > 0);
-      if (M.quote_length > 0x1F) M.quote_length = 0;
-      sen.verb_index++; sen.noun_index++; sen.capital_index++;
-      if ((P8_PW.type & W_Verb) != 0) { sen.verb_index = 0; word_copy(sen.last_verb, P8_PW); }
-      if ((P8_PW.type & W_Noun) != 0) { sen.noun_index = 0; word_copy(sen.last_noun, P8_PW); }
-      if (sen.word_count > 1 && M.last_upper < M.word_length[1]) { sen.capital_index = 0; word_copy(sen.last_capital, P8_PW); }
-    }
     bool skip = false;
     int stage = 0;   // fall-through emulation: 1 = sentence end, 2 = segment end, 3 = new line, 4 = white space
     switch (c) {
@@ -213,6 +134,8 @@ P8_HD inline void text_update(State& S) {
       tseg(M, 0).num_count++; tsen(M, 0).num_count++;
     }
   }
+P8_HD inline void text_tail(State& S, u8 c) {
+  TextM& M = S.text;
   if (M.last_newline == 1) M.first_char = (M.lang_id != LANG_UNKNOWN) ? c : (u8)imin(c, 96);
   if (M.last_nest > 512) M.nest_hash = 0;
   int lead = 0;
@@ -223,6 +146,128 @@ P8_HD inline void text_update(State& S) {
   M.mask_punct = (u32)(bp[','] > bp['.']) | ((u32)(bp[','] > bp['!']) << 1) | ((u32)(bp[','] > bp['?']) << 2) | ((u32)(bp[','] > bp[':']) << 3) | ((u32)(bp[','] > bp[';']) << 4);
   S.st_text_first = M.first_letter;
   S.st_text_mask = (u8)(M.masks[1] & 0xFF);
+}
+P8_HD inline int text_update_a(State& S) {
+  const Tables& T = *S.T;
+  TextM& M = S.text;
+  M.last_upper = umin(0xFF, M.last_upper + 1); M.mask_upper <<= 1;
+  M.last_letter = umin(0x1F, M.last_letter + 1);
+  M.last_digit = umin(0xFF, M.last_digit + 1);
+  M.last_punct = umin(0x3F, M.last_punct + 1);
+  M.last_newline++; M.prev_newline++; M.last_nest++;
+  M.space_count -= (M.spaces >> 31); M.spaces <<= 1;
+  M.masks[0] <<= 2; M.masks[1] <<= 2; M.masks[2] <<= 4; M.masks[3] <<= 3;
+  M.pstate = M.state;
+  u8 c = (u8)buf(S, 1), pC = (u8)lower(c);
+  const u8 g = (c < 0x80) ? T.ascii_group[c] : 31;
+  if (!((g <= 4) && g == (M.ascii_mask & 0x1f))) M.ascii_mask = ((M.ascii_mask << 5) | g) & ((1ull << 60) - 1);
+  M.masks[4] = (u32)(M.ascii_mask & ((1u << 30) - 1));
+  M.byte_pos[c] = (u32)S.pos;
+  if (c != pC) { c = pC; M.last_upper = 0; M.mask_upper |= 1; }
+  pC = (u8)buf(S, 2);
+  M.state = TP_Unknown;
+  M.parse_ctx = hash(sx(M.state), P8_PW.hash[1], c, (u64)((ilog2(M.last_newline) + 1) * (M.last_newline * 3 > M.prev_newline)), (u64)(M.masks[1] & 0xFC));
+  if ((c >= 'a' && c <= 'z') || c == '\'' || c == '-' || c > 0x7F) {
+    if (M.word_length[0] == 0) {
+      if (pC == 0x0A && ((M.last_letter == 3 && buf(S, 3) == '+') || (M.last_letter == 4 && buf(S, 3) == 0x0D && buf(S, 4) == '+'))) {
+        M.word_length[0] = M.word_length[1];
+        for (int i = LANG_UNKNOWN; i < LANG_COUNT; ++i) M.words_index[i]--;
+        // cWord = pWord, pWord = &Words[Lang.pId](1): as (lang, i) pairs relative to the decremented indices
+        M.cw_lang = M.pw_lang; M.cw_slot = M.pw_slot;
+        M.pw_lang = M.lang_pid; M.pw_slot = slot_of(M, M.lang_pid, 1);
+        P8_CW.clear();
+        for (u32 i = 0; i < M.word_length[0]; ++i) P8_CW.append(buf(S, (int)(M.word_length[0] - i + M.last_letter)));
+        M.word_length[1] = P8_PW.len();
+        tseg(M, 0).word_count--;
+        tsen(M, 0).word_count--;
+      } else { M.word_gap = M.last_letter; M.first_letter = c; }
+    }
+    M.last_letter = 0;
+    M.word_length[0]++;
+    M.masks[0] += (M.lang_id != LANG_UNKNOWN) ? 1 + (u32)lang_vowel(M.lang_id, c) : 1; M.masks[1]++; M.masks[3] += M.masks[0] & 3;
+    if (c == '\'') {
+      M.masks[2] += 12;
+      if (M.word_length[0] == 1) {
+        if (M.quote_length == 0 && pC == 0x20) M.quote_length = 1;
+        else if (M.quote_length > 0 && M.last_punct == 1) { M.quote_length = 0; M.state = TP_AfterQuote; M.parse_ctx = hash(sx(M.state), pC); }
+      }
+    }
+    P8_CW.append(c);
+    P8_CW.get_hashes();
+    M.state = TP_ReadingWord;
+    M.parse_ctx = hash(sx(M.state), P8_CW.hash[1]);
+    text_tail(S, c);
+    return 0;
+  }
+  if (P8_CW.len() > 0) {
+    if (M.lang_id != LANG_UNKNOWN) word_copy(tw(M, LANG_UNKNOWN, 0), P8_CW);
+    // The reference stems the German, French, English copy in this order, each copied from cWord right before (:3227-3236).
+    // When cWord is itself the current word of list `split`, that list's stemmer rewrites it and the lists below copy
+    // the rewritten word: they form a second round (text_stem_mid copies for them).
+    const int split = (M.cw_slot == slot_of(M, M.cw_lang, 0)) ? M.cw_lang : 0;
+    M.stem_split = (u8)split;
+    for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i) {
+      M.lang_count[i - 1] -= (u32)(M.lang_mask[i - 1] >> 63); M.lang_mask[i - 1] <<= 1;
+      if (i >= split && i != M.lang_id) word_copy(tw(M, i, 0), P8_CW);
+    }
+    return 1;
+  }
+  text_else_rest(S, c, pC);
+  text_tail(S, c);
+  return 0;
+}
+P8_HD inline void text_stem(State& S, int i) {   // i = LANG_EN .. LANG_DE
+  TextM& M = S.text;
+  Word& w = tw(M, i, 0);
+  M.stem_ok[i - 1] = (u8)(i == LANG_EN ? StemEN::stem(w) : i == LANG_FR ? StemFR::stem(w) : StemDE::stem(w));
+}
+P8_HD inline void text_stem_mid(State& S) {      // between the rounds: the lists below `split` copy the rewritten cWord
+  TextM& M = S.text;
+  for (int i = (int)M.stem_split - 1; i > LANG_UNKNOWN; --i)
+    if (i != M.lang_id) word_copy(tw(M, i, 0), P8_CW);
+}
+P8_HD inline void text_update_b(State& S) {
+  TextM& M = S.text;
+  const u8 c = (u8)lower((u8)buf(S, 1)), pC = (u8)buf(S, 2);
+  for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i)
+    if (M.stem_ok[i - 1]) { M.lang_count[i - 1]++; M.lang_mask[i - 1] |= 1; }
+  {
+      M.lang_id = LANG_UNKNOWN;
+      u32 best = 4;
+      for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i) {
+        if (M.lang_count[i - 1] >= best) { best = M.lang_count[i - 1] + (i == M.lang_pid); M.lang_id = i; }
+        M.words_index[i]++;
+      }
+      M.words_index[LANG_UNKNOWN]++;
+      M.lang_pid = M.lang_id;
+      M.pw_lang = M.cw_lang = M.lang_id; M.pw_slot = slot_of(M, M.lang_id, 1); M.cw_slot = slot_of(M, M.lang_id, 0);
+      P8_CW.clear();
+      M.word_pos[P8_PW.hash[1] & 0xffff] = (u32)S.pos;
+      Segment& seg = tseg(M, 0);
+      Sentence& sen = tsen(M, 0);
+      if (seg.word_count == 0) word_copy(seg.first_word, P8_PW);
+      seg.word_count++;
+      if (sen.word_count == 0) word_copy(sen.first_word, P8_PW);
+      sen.word_count++;
+      M.word_length[1] = M.word_length[0]; M.word_length[0] = 0;
+      M.quote_length += (M.quote_length > 0);
+      if (M.quote_length > 0x1F) M.quote_length = 0;
+      sen.verb_index++; sen.noun_index++; sen.capital_index++;
+      if ((P8_PW.type & W_Verb) != 0) { sen.verb_index = 0; word_copy(sen.last_verb, P8_PW); }
+      if ((P8_PW.type & W_Noun) != 0) { sen.noun_index = 0; word_copy(sen.last_noun, P8_PW); }
+      if (sen.word_count > 1 && M.last_upper < M.word_length[1]) { sen.capital_index = 0; word_copy(sen.last_capital, P8_PW); }
+      }
+  text_else_rest(S, c, pC);
+  text_tail(S, c);
+}
+P8_HD inline void text_update(State& S) {
+  if (text_update_a(S)) {
+    const int split = S.text.stem_split;
+    for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN && i >= split; --i) text_stem(S, i);
+    text_stem_mid(S);
+    for (int i = split - 1; i > LANG_UNKNOWN; --i) text_stem(S, i);
+    text_update_b(S);
+  }
 }
 
 // The 33 contexts of the text model's history map (:3376-3515). Pure apart from the sets: with sel.lanes > 1 every lane of a warp walks
