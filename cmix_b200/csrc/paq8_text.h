@@ -75,6 +75,15 @@ struct Word {   // paq8.cpp:1547-1622
   }
 };
 
+// Tables of suffixes / words walked in a loop keep the length and the deciding character of every entry next to the string, so
+// that a candidate that cannot match costs no read of the string itself (on the device the strings live in global memory).
+P8_HD inline bool ends_tab(const Word& w, const char* suf, int n, char last) {      // == w.ends(suf) with n = strlen(suf), last = suf[n-1]
+  return w.len() > (u32)n && w.L[w.e] == (u8)last && bytes_eq(&w.L[w.e - n + 1], suf, n - 1);
+}
+P8_HD inline bool is_tab(const Word& w, const char* word, int n, char first) {      // == w.is(word) with n = strlen(word), first = word[0]
+  return (int)(w.e - w.s + (w.L[w.s] != 0)) == n && w.L[w.s] == (u8)first && bytes_eq(&w.L[w.s], word, n);
+}
+
 // Stemmer::GetRegion / SuffixInRn (paq8.cpp:1731-1746) with the language's vowel set
 P8_HD inline u32 region(const Word& w, u32 from, const char* vowels) {
   bool seen = false;
@@ -191,14 +200,16 @@ struct StemEN {
   }
   P8_HD static bool step1b(Word& w, u32 r1) {
     const char* suf[6] = {"eedly", "eed", "ed", "edly", "ing", "ingly"};
+    const u8 len[6] = {5, 3, 2, 4, 3, 5};
+    const char last[6] = {'y', 'd', 'd', 'y', 'g', 'y'};
     const u64 typ[6] = {EN_AdverbOfManner, 0, EN_PastTense, EN_AdverbOfManner | EN_PastTense, EN_PresentParticiple, EN_AdverbOfManner | EN_PresentParticiple};
     for (int i = 0; i < 6; ++i) {
-      if (!w.ends(suf[i])) continue;
+      if (!ends_tab(w, suf[i], len[i], last[i])) continue;
       if (i < 2) {
-        if (in_rn(w, r1, cstrlen(suf[i]))) w.e -= 1 + i * 2;
+        if (in_rn(w, r1, len[i])) w.e -= 1 + i * 2;
       } else {
         const u8 keep = w.e;
-        w.e -= cstrlen(suf[i]);
+        w.e -= len[i];
         if (!has_vowel(w)) { w.e = keep; return false; }
         if (w.ends("at") || w.ends("bl") || w.ends("iz") || short_word(w)) w.append('e');
         else if (w.len() > 2) {
@@ -262,8 +273,10 @@ struct StemEN {
     const u64 typ[22] = {EN_ION, EN_ION | EN_AL, EN_NESS, EN_NESS, EN_NESS, EN_ION | EN_AL, EN_AdverbOfManner, EN_AdverbOfManner | EN_ITY,
                          EN_AdverbOfManner, EN_ION, 0, EN_ITY, EN_AdverbOfManner, EN_AdverbOfManner, EN_ITY, 0, 0, EN_AdverbOfManner, 0, 0,
                          EN_AdverbOfManner, EN_AdverbOfManner};
+    const u8 len[22] = {7, 7, 7, 7, 7, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 4, 4, 4, 4, 4, 4, 3};
+    const char last[22] = {'n', 'l', 's', 's', 's', 'l', 'i', 'i', 'i', 'n', 'm', 'i', 'i', 'i', 'i', 'i', 'i', 'i', 'r', 'r', 'i', 'i'};
     for (int i = 0; i < 22; ++i)
-      if (w.ends(from[i]) && in_rn(w, r1, cstrlen(from[i]))) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; return true; }
+      if (ends_tab(w, from[i], len[i], last[i]) && in_rn(w, r1, len[i])) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; return true; }
     if (w.ends("logi") && in_rn(w, r1, 3)) { --w.e; return true; }
     if (w.ends("li")) {
       if (in_rn(w, r1, 2) && in_set(w.rat(2), "cdeghkmnrt")) { w.e -= 2; w.type |= EN_AdverbOfManner; return true; }
@@ -285,8 +298,10 @@ struct StemEN {
     const char* to[8] = {"ate", "tion", "al", "ic", "ic", "ic", "", ""};
     const u64 typ[8] = {EN_ION | EN_AL, EN_ION | EN_AL, 0, 0, EN_ITY, EN_AL, EN_AdjFull, EN_NESS};
     bool r = false;
+    const u8 len[8] = {7, 6, 5, 5, 5, 4, 3, 4};
+    const char last[8] = {'l', 'l', 'e', 'e', 'i', 'l', 'l', 's'};
     for (int i = 0; i < 8; ++i)
-      if (w.ends(from[i]) && in_rn(w, r1, cstrlen(from[i]))) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; r = true; break; }
+      if (ends_tab(w, from[i], len[i], last[i]) && in_rn(w, r1, len[i])) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; r = true; break; }
     if (w.ends("ative") && in_rn(w, r2, 5)) { w.e -= 5; w.type |= EN_IVE; return true; }
     if (w.len() > 5 && w.ends("less")) { w.e -= 4; w.type |= EN_AdjWithout; return true; }
     return r;
@@ -296,9 +311,11 @@ struct StemEN {
                            "ive", "ize", "sion", "tion"};
     const u64 typ[20] = {EN_AL, EN_NCE, EN_NCE, 0, EN_IC, EN_Capable, EN_Capable, EN_NT, 0, 0, EN_NT, 0, 0, 0, EN_ITY, EN_OUS, EN_IVE, 0, EN_ION, EN_ION};
     bool r = false;
+    const u8 len[20] = {2, 4, 4, 2, 2, 4, 4, 3, 5, 4, 3, 2, 3, 3, 3, 3, 3, 3, 4, 4};
+    const char last[20] = {'l', 'e', 'e', 'r', 'c', 'e', 'e', 't', 't', 't', 't', 'u', 'm', 'e', 'i', 's', 'e', 'e', 'n', 'n'};
     for (int i = 0; i < 20; ++i) {
-      if (w.ends(suf[i]) && in_rn(w, r2, cstrlen(suf[i]))) {
-        w.e -= (u8)(cstrlen(suf[i]) - (i > 17));
+      if (ends_tab(w, suf[i], len[i], last[i]) && in_rn(w, r2, len[i])) {
+        w.e -= (u8)(len[i] - (i > 17));
         if (i != 10 || w.rat(0) != 'm') w.type |= typ[i];
         if (i == 0 && w.ends("nti")) { --w.e; r = true; continue; }
         return true;
@@ -328,8 +345,10 @@ struct StemEN {
       const char* b[11] = {"ski", "sky", "die", "lie", "tie", "idle", "gentle", "ugli", "earli", "onli", "singl"};
       const u64 t[18] = {W_Noun | EN_Plural, EN_Plural, EN_PresentParticiple, EN_PresentParticiple, EN_PresentParticiple, EN_AdverbOfManner,
                          EN_AdverbOfManner, EN_Adjective, EN_Adjective | EN_AdverbOfManner, 0, EN_AdverbOfManner, W_Noun, W_Noun, 0, W_Noun, W_Noun, W_Noun, 0};
+      const u8 len[18] = {4, 5, 5, 5, 5, 4, 6, 4, 5, 4, 6, 3, 4, 4, 5, 6, 4, 5};
+      const char first[18] = {'s', 's', 'd', 'l', 't', 'i', 'g', 'u', 'e', 'o', 's', 's', 'n', 'h', 'a', 'c', 'b', 'a'};
       for (int i = 0; i < 18; ++i)
-        if (w.is(a[i])) {
+        if (is_tab(w, a[i], len[i], first[i])) {
           if (i < 11) { const int n = cstrlen(b[i]); for (int k = 0; k < n; ++k) w.L[w.s + k] = (u8)b[i][k]; w.e = (u8)(w.s + (u8)(n - 1)); }
           rehash(w);
           w.type |= t[i];
@@ -344,8 +363,10 @@ struct StemEN {
     r |= step1a(w);
     {
       const char* a[8] = {"inning", "outing", "canning", "herring", "earring", "proceed", "exceed", "succeed"};
+      const u8 len[8] = {6, 6, 7, 7, 7, 7, 6, 7};
+      const char first[8] = {'i', 'o', 'c', 'h', 'e', 'p', 'e', 's'};
       for (int i = 0; i < 8; ++i)
-        if (w.is(a[i])) { rehash(w); w.type |= i < 5 ? W_Noun : W_Verb; w.language = LANG_EN; return r; }
+        if (is_tab(w, a[i], len[i], first[i])) { rehash(w); w.type |= i < 5 ? W_Noun : W_Verb; w.language = LANG_EN; return r; }
     }
     r |= step1b(w, r1);
     r |= step1c(w);
@@ -355,10 +376,10 @@ struct StemEN {
     r |= step5(w, r1, r2);
     for (u8 i = w.s; i <= w.e; ++i) if (w.L[i] == 'Y') w.L[i] = 'y';
     if (!w.type || w.type == EN_Plural) {
-      if (w.any_of("he|him|his|himself|man|men|boy|husband|actor")) { r = true; w.type |= EN_Male; }
-      else if (w.any_of("she|her|herself|woman|women|girl|wife|actress")) { r = true; w.type |= EN_Female; }
+      if ((w.is("he") || w.is("him") || w.is("his") || w.is("himself") || w.is("man") || w.is("men") || w.is("boy") || w.is("husband") || w.is("actor"))) { r = true; w.type |= EN_Male; }
+      else if ((w.is("she") || w.is("her") || w.is("herself") || w.is("woman") || w.is("women") || w.is("girl") || w.is("wife") || w.is("actress"))) { r = true; w.type |= EN_Female; }
     }
-    if (!r) r = w.any_of("the|be|to|of|and|in|that|you|have|with|from|but");
+    if (!r) r = (w.is("the") || w.is("be") || w.is("to") || w.is("of") || w.is("and") || w.is("in") || w.is("that") || w.is("you") || w.is("have") || w.is("with") || w.is("from") || w.is("but"));
     rehash(w);
     if (r) w.language = LANG_EN;
     return r;
@@ -549,7 +570,7 @@ struct StemFR {
       r |= s6;
     }
     for (int i = w.s; i <= w.e; ++i) w.L[i] = (u8)lower(w.L[i]);
-    if (!r) r = w.any_of("de|la|le|et|en|un|une|du|que|pas");
+    if (!r) r = (w.is("de") || w.is("la") || w.is("le") || w.is("et") || w.is("en") || w.is("un") || w.is("une") || w.is("du") || w.is("que") || w.is("pas"));
     rehash(w);
     if (r) w.language = LANG_FR;
     return r;
@@ -658,7 +679,7 @@ struct StemDE {
         default: w.L[i] = (u8)lower(w.L[i]);
       }
     }
-    if (!r) r = w.any_of("der|die|das|und|sie|ich|mit|sich|auf|nicht");
+    if (!r) r = (w.is("der") || w.is("die") || w.is("das") || w.is("und") || w.is("sie") || w.is("ich") || w.is("mit") || w.is("sich") || w.is("auf") || w.is("nicht"));
     rehash(w);
     if (r) w.language = LANG_DE;
     return r;
@@ -667,7 +688,7 @@ struct StemDE {
 
 P8_HD inline bool lang_vowel(int lang, int c) { return lang == LANG_EN ? StemEN::vowel(c) : lang == LANG_FR ? StemFR::vowel(c) : StemDE::vowel(c); }
 P8_HD inline bool lang_abbrev(int lang, const Word& w) {
-  return lang == LANG_EN ? w.any_of("mr|mrs|ms|dr|st|jr") : lang == LANG_FR ? w.any_of("m|mm") : w.any_of("fr|hr|hrn");
+  return lang == LANG_EN ? (w.is("mr") || w.is("mrs") || w.is("ms") || w.is("dr") || w.is("st") || w.is("jr")) : lang == LANG_FR ? (w.is("m") || w.is("mm")) : (w.is("fr") || w.is("hr") || w.is("hrn"));
 }
 
 }  // namespace p8
