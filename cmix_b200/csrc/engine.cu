@@ -291,6 +291,9 @@ struct cmixb200_predictor {
   cudaStream_t s_ppmd = nullptr; float* d_ppmd_gen = nullptr; size_t ppmd_gen_bytes = 0;   // resident PPMD: own stream, scratch [n_bytes][256]
   PpmdModel* d_ppmd_model = nullptr;
   cudaEvent_t ev_lock_mix = nullptr, ev_lock_small = nullptr, ev_lock_p8 = nullptr, ev_lock_bit = nullptr;   // lock-step: order the library streams per bit
+  DecodeState* d_dec = nullptr;                      // device decoder (cmixb200_decode_bytes)
+  cudaGraphExec_t dec_graph[3] = {nullptr, nullptr, nullptr};  // a bit inside a byte / the bit that completes a byte / the last bit of a call
+  cudaEvent_t ev_dec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   CoderState* d_coder = nullptr; u8* d_code = nullptr; size_t code_cap = 0; bool coder_on = false;
   // lock-step state
   u64 bits_done = 0;                   // coded bits so far (Mixer::steps_)
@@ -942,6 +945,9 @@ void cmixb200_destroy(cmixb200_predictor* P) {
   if (P->ev_lock_small) cudaEventDestroy(P->ev_lock_small);
   if (P->ev_lock_p8) cudaEventDestroy(P->ev_lock_p8);
   if (P->ev_lock_bit) cudaEventDestroy(P->ev_lock_bit);
+  for (auto& g : P->dec_graph) if (g) cudaGraphExecDestroy(g);
+  for (auto& ev : P->ev_dec) if (ev) cudaEventDestroy(ev);
+  if (P->d_dec) cudaFree(P->d_dec);
   if (P->d_coder) cudaFree(P->d_coder);
   if (P->d_code) cudaFree(P->d_code);
   if (P->s_ppmd) cudaStreamDestroy(P->s_ppmd);
@@ -1064,55 +1070,123 @@ int cmixb200_perceive(cmixb200_predictor* P, int bit) {
   return CMIXB200_OK;
 }
 
-// Decoder::Decode for n_bytes on the device: predict kernels, one arithmetic-decoder step, perceive kernels,
-// bit after bit without a host round trip; the host only queues launches and waits once at the end.
+// One bit of the decode loop as a CUDA graph: decoder step for the standing prediction, perceive on three streams, then the
+// predict kernels of the NEXT bit (its producers overlap the tail of FXCM / PAQ8), join. Launches of the graph on s_mix run one
+// after the other, so no event crosses from one bit to the next.
+static int BuildDecodeGraph(cmixb200_predictor* P, bool byte_done, bool next_predict, cudaGraphExec_t* out) {
+  const Tables T = P->T;
+  const u32* dbit = reinterpret_cast<const u32*>(P->d_dec);
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(P->s_mix, cudaStreamCaptureModeThreadLocal));
+  bool ok = true;
+  auto chk = [&](cudaError_t ce) { if (ce != cudaSuccess && ok) { ok = false; g_last_error = std::string("decode graph: ") + cudaGetErrorString(ce); } };
+  // the decoder step for the prediction already standing in last_p, then the perceive kernels of that bit ...
+  decode_step_kernel<<<1, 1, 0, P->s_mix>>>(P->d_st, P->d_dec);
+  chk(cudaEventRecord(P->ev_dec[2], P->s_mix));
+  chk(cudaStreamWaitEvent(P->s_small, P->ev_dec[2], 0));
+  chk(cudaStreamWaitEvent(P->s_p8, P->ev_dec[2], 0));
+  const float* ppmd = byte_done ? P->d_ppmd_byte : nullptr;
+  if (byte_done) {
+    ppmd_byte_kernel<<<1, 32, sizeof(PpmdWarpShared), P->s_small>>>(P->d_st, 0, P->d_ppmd_byte, dbit);
+    chk(cudaEventRecord(P->ev_dec[3], P->s_small));
+    chk(cudaStreamWaitEvent(P->s_mix, P->ev_dec[3], 0));
+  }
+  small_perceive_kernel<<<1, 64, 0, P->s_small>>>(P->d_st, 0, ppmd, 0, dbit);
+  mix_perceive_kernel<<<N_L0 + 2, MIX_THREADS, 0, P->s_mix>>>(P->d_st, 0, 0.0f, dbit);
+  if (byte_done) lstm_byte_kernel<<<LSTM_CTAS, LSTM_THREADS, sizeof(LstmShared), P->s_mix>>>(P->d_st, 0, ppmd, dbit);
+  chk(cudaEventRecord(P->ev_dec[0], P->s_mix));           // the LSTM's read-out state is final
+  fxcm_launch_bit(P->d_st, P->d_fx, 0, 0, P->d_ext_bit, P->s_mix, dbit);
+  paq8_launch_bit(P->d_p8, 0, P->d_ext_bit, P->s_p8, dbit);
+  chk(cudaEventRecord(P->ev_dec[5], P->s_p8));
+  chk(cudaEventRecord(P->ev_dec[4], P->s_small));
+  if (next_predict) {
+    // ... and the predict kernels of the next bit: the producers start while FXCM and PAQ8 are still perceiving
+    chk(cudaStreamWaitEvent(P->s_small, P->ev_dec[0], 0));
+    lock_predict_inputs_kernel<<<2, 64, 0, P->s_small>>>(P->d_st, T);
+    chk(cudaEventRecord(P->ev_dec[1], P->s_small));
+    chk(cudaStreamWaitEvent(P->s_mix, P->ev_dec[1], 0));
+    chk(cudaStreamWaitEvent(P->s_mix, P->ev_dec[5], 0));
+    mix_predict_rows_kernel<<<N_L0, 256, 0, P->s_mix>>>(P->d_st, T, P->d_ext_bit);
+    mix_predict_final_kernel<<<1, MIX_THREADS, sizeof(MixShared), P->s_mix>>>(P->d_st, T);
+  } else {                       // the last bit of a call: no prediction is left standing (a bulk call or Predict() may follow)
+    chk(cudaStreamWaitEvent(P->s_mix, P->ev_dec[4], 0));
+    chk(cudaStreamWaitEvent(P->s_mix, P->ev_dec[5], 0));
+  }
+  const cudaError_t ce = cudaStreamEndCapture(P->s_mix, &graph);
+  if (ce != cudaSuccess || !ok || !graph) { if (ok) g_last_error = std::string("decode graph: ") + cudaGetErrorString(ce); if (graph) cudaGraphDestroy(graph); return CMIXB200_ERR_CUDA; }
+  const cudaError_t ci = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess) { g_last_error = std::string("decode graph: ") + cudaGetErrorString(ci); return CMIXB200_ERR_CUDA; }
+  return CMIXB200_OK;
+}
+
+// Decoder::Decode for n_bytes on the device: per bit one graph launch = predict kernels, one arithmetic-decoder
+// step, perceive kernels; the bit never visits the host, which only queues the launches and waits once per 1 024 bits.
 int cmixb200_decode_bytes(cmixb200_predictor* P, const uint8_t* archive, size_t n_archive, uint8_t* out, size_t n_bytes) {
   CK(cudaSetDevice(P->device));
   if (!archive || !out) { g_last_error = "decode_bytes: null argument"; return CMIXB200_ERR_ARG; }
   if (P->bit_context != 1) { g_last_error = "decode_bytes: the stream must stand on a byte boundary"; return CMIXB200_ERR_ARG; }
-  if ((P->replay_mask & (CMIXB200_REPLAY_FXCM | CMIXB200_REPLAY_PAQ8)) != 0) { g_last_error = "decode_bytes needs every model group resident"; return CMIXB200_ERR_ARG; }
+  if (!P->d_fx || !P->d_p8) { g_last_error = "decode_bytes needs every model group resident"; return CMIXB200_ERR_ARG; }
   if (n_bytes == 0) return CMIXB200_OK;
+  const size_t n_bits = n_bytes * 8;
+  // all library streams idle: a lock-step Perceive() or a bulk call may still be in flight
+  CK(cudaStreamSynchronize(P->s_small)); CK(cudaStreamSynchronize(P->s_mix)); CK(cudaStreamSynchronize(P->s_p8));
+  if (P->s_fx) CK(cudaStreamSynchronize(P->s_fx));
+  if (!P->d_dec) {
+    CK(cudaMalloc(&P->d_dec, sizeof(DecodeState)));
+    for (auto& ev : P->ev_dec) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    TRY(BuildDecodeGraph(P, false, true, &P->dec_graph[0]));
+    TRY(BuildDecodeGraph(P, true, true, &P->dec_graph[1]));
+    TRY(BuildDecodeGraph(P, true, false, &P->dec_graph[2]));
+  }
   u8 *d_arch = nullptr, *d_out = nullptr;
-  DecodeState* d_ds = nullptr;
+  float* d_decay = nullptr;
   int r = CMIXB200_OK;
   auto fail = [&](const char* what) { g_last_error = std::string("decode_bytes: ") + what; r = CMIXB200_ERR_CUDA; };
-  if (cudaMalloc(&d_arch, n_archive ? n_archive : 1) != cudaSuccess || cudaMalloc(&d_out, n_bytes) != cudaSuccess || cudaMalloc(&d_ds, sizeof(DecodeState)) != cudaSuccess) fail("out of device memory");
+  if (cudaMalloc(&d_arch, n_archive ? n_archive : 1) != cudaSuccess || cudaMalloc(&d_out, n_bytes) != cudaSuccess ||
+      cudaMalloc(&d_decay, n_bits * sizeof(float)) != cudaSuccess) fail("out of device memory");
   if (r == CMIXB200_OK) {
+    std::vector<float> decay(n_bits);
+    for (size_t t = 0; t < n_bits; ++t) decay[t] = 0.9 / pow(0.0000001 * (unsigned long long)(P->bits_done + t) + 0.8, 0.8);   // mixer.cpp:58, as cmixb200_perceive
     DecodeState h;
     memset(&h, 0, sizeof h);
-    h.n_arch = n_archive; h.arch = d_arch; h.out = d_out;
-    if (cudaMemcpyAsync(d_arch, archive, n_archive, cudaMemcpyHostToDevice, P->s_mix) != cudaSuccess ||
-        cudaMemcpyAsync(d_ds, &h, sizeof h, cudaMemcpyHostToDevice, P->s_mix) != cudaSuccess) fail("upload failed");
-    else decode_begin_kernel<<<1, 1, 0, P->s_mix>>>(d_ds);
+    h.n_arch = n_archive; h.arch = d_arch; h.out = d_out; h.decay = d_decay;
+    if (cudaMemcpy(d_arch, archive, n_archive, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_decay, decay.data(), n_bits * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(P->d_dec, &h, sizeof h, cudaMemcpyHostToDevice) != cudaSuccess) fail("upload failed");
+    else {
+      decode_begin_kernel<<<1, 1, 0, P->s_mix>>>(P->d_dec);
+      r = LaunchPredict(P);                  // the first prediction; every graph leaves the next one standing
+      if (r == CMIXB200_OK && cudaStreamSynchronize(P->s_mix) != cudaSuccess) fail("first prediction failed");
+    }
   }
-  const u32* dbit = reinterpret_cast<const u32*>(d_ds);
-  for (size_t t = 0; r == CMIXB200_OK && t < n_bytes * 8; ++t) {
-    r = LaunchPredict(P);
-    if (r != CMIXB200_OK) break;
-    decode_step_kernel<<<1, 1, 0, P->s_mix>>>(P->d_st, d_ds);
-    P->launches++;
-    r = LaunchPerceive(P, 0, 0, (t & 7) == 7, dbit);
-    if ((t & 7) == 7) P->ppmd_byte_valid = false;
-    if ((t & 1023) == 1023 && r == CMIXB200_OK) {      // bound the launch queue and surface device errors early
-      const cudaError_t ce = cudaStreamSynchronize(P->s_mix);
-      if (ce != cudaSuccess) fail(cudaGetErrorString(ce));
+  for (size_t t = 0; r == CMIXB200_OK && t < n_bits; ++t) {
+    const cudaError_t ce = cudaGraphLaunch(P->dec_graph[t + 1 == n_bits ? 2 : ((t & 7) == 7 ? 1 : 0)], P->s_mix);
+    if (ce != cudaSuccess) { fail(cudaGetErrorString(ce)); break; }
+    if ((t & 1023) == 1023) {      // bound the launch queue and surface device errors early
+      const cudaError_t cs = cudaStreamSynchronize(P->s_mix);
+      if (cs != cudaSuccess) fail(cudaGetErrorString(cs));
     }
   }
   if (r == CMIXB200_OK) {
-    cudaError_t ce = cudaStreamSynchronize(P->s_mix);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(P->s_small);
-    if (ce == cudaSuccess && P->s_p8) ce = cudaStreamSynchronize(P->s_p8);
-    if (ce != cudaSuccess) fail(cudaGetErrorString(ce));
+    const cudaError_t cs = cudaStreamSynchronize(P->s_mix);
+    if (cs != cudaSuccess) fail(cudaGetErrorString(cs));
     else if (cudaMemcpy(out, d_out, n_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) fail("download failed");
   }
-  if (r == CMIXB200_OK) r = CheckPaq8(P);
+  if (r == CMIXB200_OK) {
+    P->bits_done += n_bits;
+    P->launches += n_bits * 9 + n_bytes * 2;
+    P->ppmd_byte_valid = false;
+    CK(cudaEventRecord(P->ev_lock_mix, P->s_mix));     // the next lock-step Predict() is ordered behind the loop
+    r = CheckPaq8(P);
+  }
   if (r == CMIXB200_OK && P->d_ppmd_model) {
     uint32_t err = 0;
     if (cudaMemcpy(&err, (const char*)P->d_ppmd_model + offsetof(PpmdModel, error), 4, cudaMemcpyDeviceToHost) == cudaSuccess && err) {
       g_last_error = "PPMD arena exhausted: raise CMIXB200_PPMD_MB (the reference would cut its model off here)"; r = CMIXB200_ERR_CAPACITY;
     }
   }
-  cudaFree(d_arch); cudaFree(d_out); cudaFree(d_ds);
+  cudaFree(d_arch); cudaFree(d_out); cudaFree(d_decay);
   return r;
 }
 

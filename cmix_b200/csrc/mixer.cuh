@@ -501,7 +501,11 @@ mix_predict_final_kernel(StreamState* st, Tables T) {
 // (ByteModel::Perceive, byte-model.cpp:17-30).
 __global__ void __launch_bounds__(MIX_THREADS, 1)
 mix_perceive_kernel(StreamState* st, int bit, float decay_base, const u32* dbit = nullptr) {
-  if (dbit) bit = (int)dbit[0];          // decode loop: the bit comes from decode_step_kernel, not from the host
+  if (dbit) {                            // decode loop: the bit and the step's decay factor come from the device
+    const DecodeState* ds = reinterpret_cast<const DecodeState*>(dbit);
+    bit = (int)ds->bit;
+    if (ds->decay) decay_base = ds->decay[ds->t - 1];
+  }
   __shared__ float upd[N_L1 + 2];
   __shared__ u32 shrink[N_L1 + 2];
   const int tid = threadIdx.x, blk = blockIdx.x;

@@ -176,6 +176,7 @@ struct DecodeState {
   u32 x1, x2, x, ctx;           // Decoder::x1_, x2_, x_ (decoder.cpp:3-8); bits of the current byte with a leading 1
   u64 pos, n_arch, t;           // next archive byte, archive length, bits decoded
   const u8* arch; u8* out;
+  const float* decay;           // [bit of this call] the mixers' learning-rate factor 0.9 / pow(1e-7 * steps + 0.8, 0.8), host-built (glibc pow)
 };
 
 struct ChunkArgs {

@@ -126,3 +126,17 @@ def test_everything_resident_lock_step(cm):
     rest = P.code_bytes(g["stream"][n:512], None, None)
     P.close()
     assert np.array_equal(rest, g["p"][n * 8:512 * 8])
+
+
+@pytest.mark.gpu
+def test_unmodelled_block_fails_loudly(cm):
+    """PAQ8's image / audio / JPEG sub-models are not resident: a stream in which its block parser would validate such a header
+    must make the call fail (CMIXB200_ERR_UNSUPPORTED), never return different predictions silently."""
+    g = _load("full_text")
+    text = g["stream"][:700].copy()
+    jpeg = np.frombuffer(bytes([0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10]) + b"JFIF\x00\x01\x01\x00\x00\x01\x00\x01\x00\x00", dtype=np.uint8)
+    stream = np.concatenate([text[:300], jpeg, text[300:]])
+    P = cm.Predictor(np.ones(256, dtype=np.uint8))
+    with pytest.raises(RuntimeError, match="image / audio / JPEG"):
+        P.code_bytes(stream, None, None)
+    P.close()
