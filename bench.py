@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_STREAMS", "1")), help="independent files per GPU for `value`")
-    ap.add_argument("--aggregate-streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_AGG", "6")), help="files per GPU for the aggregate figure (0 = skip)")
+    ap.add_argument("--aggregate-streams", type=int, default=int(os.environ.get("CMIXB200_BENCH_AGG", "7")), help="files per GPU for the aggregate figure (0 = skip)")
     ap.add_argument("--step-bytes", type=int, default=1024)
     ap.add_argument("--cpu-sample-bytes", type=int, default=4096)
     args = ap.parse_args()

@@ -1289,9 +1289,12 @@ int cmixb200_code_batch(cmixb200_predictor** preds, int n_streams, const uint8_t
     for (int s = 0; s < n_streams; ++s) {
       db[s] = preds[s]->d_bytes2[k]; de[s] = preds[s]->d_ext2[k]; dp[s] = preds[s]->d_ppmd2[k]; dout[s] = preds[s]->d_p;
     }
-    TRY(RunPipelined(preds, n_streams, db.data(), n, ext ? de.data() : nullptr, ppmd ? dp.data() : nullptr, dout.data(), false));
+    const int rr = RunPipelined(preds, n_streams, db.data(), n, ext ? de.data() : nullptr, ppmd ? dp.data() : nullptr, dout.data(), false);
+    if (rr != CMIXB200_OK) { cudaStreamSynchronize(lead->s_copy); return rr; }   // no copy into the caller's buffers stays in flight
     for (int s = 0; s < n_streams; ++s)
-      CK(cudaMemcpyAsync(p_out[s] + off * 8, preds[s]->d_p, n * 8 * 4, cudaMemcpyDeviceToHost, lead->s_copy));
+      if (cudaMemcpyAsync(p_out[s] + off * 8, preds[s]->d_p, n * 8 * 4, cudaMemcpyDeviceToHost, lead->s_copy) != cudaSuccess) {
+        g_last_error = "code_batch: result copy failed"; cudaStreamSynchronize(lead->s_copy); return CMIXB200_ERR_CUDA;
+      }
   }
   CK(cudaStreamSynchronize(lead->s_copy));
   return CMIXB200_OK;
