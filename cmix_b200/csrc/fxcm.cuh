@@ -334,12 +334,15 @@ __global__ void __launch_bounds__(FX_THREADS, 1) fxcm_bit_kernel(StreamState* st
   FxShared& sh = *reinterpret_cast<FxShared*>(fx_raw);
   const int tid = threadIdx.x;
   const FxGlobals gl = fx_load(sh, g, tid);
+  float* probs = reinterpret_cast<float*>(sh.seen);     // free until fx_bit clears it: the 256 probabilities arrive side by side
+  if (!pretrain && tid < 256) probs[tid] = st->lstm.bm.probs[tid];
+  __syncthreads();
   if (tid == 0) {
     if (pretrain) { sh.dots[10] = sh.S.lstmpr; sh.dots[11] = sh.S.lstmex; }
     else {
       const ByteModelState& b = st->lstm.bm;
       int ex;
-      const float p = bytemodel_predict(b.probs, b.bot, b.top, &ex);
+      const float p = bytemodel_predict(probs, b.bot, b.top, &ex);     // the sums stay one serial chain (byte-model.cpp:8-24)
       sh.dots[10] = (int)(u32)XM_FADD(1.0f, XM_FMUL(4094.0f, p));
       sh.dots[11] = ex;
     }

@@ -681,8 +681,16 @@ lstm_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
 // Lock-step Predict(), producer half: CTA 0 = the 54 small models + contexts (small_models.cuh), CTA 1 = the
 // LSTM's bit read-out (ByteModel::Predict, byte-model.cpp:8-15). Independent of each other, one launch.
 __global__ void __launch_bounds__(64, 1) lock_predict_inputs_kernel(StreamState* st, Tables T) {
-  if (blockIdx.x == 1) {
-    if (threadIdx.x == 0) lstm_readout(st->lstm, T, &st->lstm_x, &st->lstm_override);
+  if (blockIdx.x == 1) {            // the LSTM's bit read-out: the 256 probabilities come in side by side, the sums stay one serial chain
+    __shared__ float probs[256];
+    ByteModelState& b = st->lstm.bm;
+    for (int i = threadIdx.x; i < 256; i += 64) probs[i] = b.probs[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float p = bytemodel_predict(probs, b.bot, b.top, &b.ex);
+      st->lstm_override = (p == 0.0f || p == 1.0f) ? p : -1.0f;
+      st->lstm_x = stretch(T, p);
+    }
     return;
   }
   __shared__ SmallShared sh;

@@ -47,3 +47,30 @@ def test_256k_text_equals_the_reference():
     pd = p.astype(np.float64)
     bpc = float(-np.log2(np.where(bits == 1, pd, 1 - pd).clip(1.0 / 65536, 1)).sum() / stream.size)
     assert abs(bpc - float(g["bpc"][0])) < 1e-9
+
+
+GOLD_1M = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long_text1m.npz")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(3600)
+@pytest.mark.skipif(os.environ.get("CMIXB200_SLOW") != "1" or not os.path.exists(GOLD_1M), reason="1 MiB run: set CMIXB200_SLOW=1 (5 minutes on a B200)")
+def test_1m_text_equals_the_reference():
+    """Same check over 1 MiB (gen_synth seed 0xE9E80011): 8.4 M coded bits, one CRC per 4 096; run on demand."""
+    import cmix_b200
+    g = np.load(GOLD_1M)
+    stream = g["stream"]
+    os.environ.setdefault("CMIXB200_PPMD_MB", "8192")
+    P = cmix_b200.Predictor(g["vocab"])
+    step = 65536
+    bad = []
+    for lo in range(0, stream.size, step):
+        p = P.code_bytes(stream[lo:lo + step])
+        crc = np.array([zlib.crc32(p[b:b + 4096].tobytes()) for b in range(0, p.size, 4096)], dtype=np.uint32)
+        want = g["crc_p"][lo * 8 // 4096:(lo + step) * 8 // 4096]
+        miss = np.nonzero(crc != want)[0]
+        if miss.size:
+            bad.append(lo * 8 // 4096 + int(miss[0]))
+            break
+    P.close()
+    assert not bad, "first differing block of 4096 bits: %d" % bad[0]
