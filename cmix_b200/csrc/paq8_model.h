@@ -76,6 +76,12 @@ P8_HD inline u32 bitcount(u32 v) {
 P8_HD inline u32 ilog2(u32 x) { x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16; return bitcount(x >> 1); }
 
 // hashes (paq8.cpp:714-776)
+// code that runs once per byte (or more rarely) stays out of line on the device: the per-bit path is instruction-fetch sensitive
+#if defined(__CUDACC__)
+#define P8_COLD __noinline__
+#else
+#define P8_COLD
+#endif
 #define P8_PHI64 0x9E3779B97F4A7C15ull
 #define P8_M1 0x993DDEFFB1462949ull
 #define P8_M2 0xE9C91DC159AB0D2Dull
@@ -266,7 +272,7 @@ P8_HD inline int bucket_find(u8* t, u32 bucket, u16 ch) {
   for (int k = 0; k < 7; ++k) e[15 + 7 * idx + k] = 0;
   return bh + 7 * idx;
 }
-P8_HD inline void deferred_histories(u8* t, u32 mask, u32 ctx, u16 chk, int cell0) {   // bits 2-7 of a context seen the second time
+P8_COLD P8_HD inline void deferred_histories(u8* t, u32 mask, u32 ctx, u16 chk, int cell0) {   // bits 2-7 of a context seen the second time
   const int c = t[cell0 + 4] + 256;
   int p = bucket_find(t, (ctx + (u32)(c >> 6)) & mask, chk);
   t[p] = (u8)(1 + ((c >> 5) & 1));
@@ -371,7 +377,7 @@ P8_HD inline int cm_step(Cm& m, int i, Out& o, int ns, int y, int c0, int bp, in
   return s > 0;
 }
 // The in-order loop. `rnd` is the global generator: draws happen in context order.
-P8_HD inline int cm_mix(Cm& m, Out& o, Rnd& rnd, int y, int c0, int bp, int c1) {
+P8_COLD P8_HD inline int cm_mix(Cm& m, Out& o, Rnd& rnd, int y, int c0, int bp, int c1) {
   const Tables& T = *o.T;
   int result = 0;
   for (int i = 0; i < m.cn; ++i) {
@@ -489,7 +495,7 @@ P8_HD inline int cm2_step(Cm2& m, int i, Out& o, int y, int bpos) {
 }
 // In-order evaluation. The reference updates ALL contexts before predicting from any (two loops); the per-context fusion
 // below is the same computation whenever the contexts touch disjoint buckets this bit, and the two-loop order otherwise.
-P8_HD inline int cm2_mix_body(Cm2& m, Out& o, int y, int bpos) {   // after cm2_begin(), before the byte-end reset of `index`
+P8_COLD P8_HD inline int cm2_mix_body(Cm2& m, Out& o, int y, int bpos) {   // after cm2_begin(), before the byte-end reset of `index`
   const Tables& T = *o.T;
   u8* t = m.t;
   // loop 1 (Update): cells and pointers only

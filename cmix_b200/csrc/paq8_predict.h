@@ -302,7 +302,7 @@ P8_HD inline void smatch_select(State& S) {   // the model's two mixer selector 
 }
 
 // ---------------------------------------------------------------- sparse / distance / pic models
-P8_HD inline void sparse_byte(State& S, int seenbefore, int howmany) {   // :4504-4535
+P8_COLD P8_HD inline void sparse_byte(State& S, int seenbefore, int howmany) {   // :4504-4535
   Cm& cm = S.sparse.cm;
   const u32 c4 = S.c4, f4 = S.f4;
   u64 i = 0;
@@ -333,7 +333,7 @@ P8_HD inline void sparse_byte(State& S, int seenbefore, int howmany) {   // :450
     cm_set(cm, hash(++i, (u64)((buf(S, j + 3) << 8) | buf(S, j + 1))));
   }
 }
-P8_HD inline void sparse1_byte(State& S, int seenbefore, int howmany) {   // :4539-4586
+P8_COLD P8_HD inline void sparse1_byte(State& S, int seenbefore, int howmany) {   // :4539-4586
   Sparse1M& M = S.sparse1;
   Cm& cm = M.cm;
   const u32 c4 = S.c4;
@@ -378,7 +378,7 @@ P8_HD inline void sparse1_byte(State& S, int seenbefore, int howmany) {   // :45
   scm_set(M.scm[3], S.spafdo * ((S.w4 & 3) == 1));
   scm_set(M.scm[6], S.frstchar);
 }
-P8_HD inline void distance_byte(State& S) {   // :4598-4611
+P8_COLD P8_HD inline void distance_byte(State& S) {   // :4598-4611
   DistanceM& M = S.distance;
   const int c = (int)(S.c4 & 0xff);
   if (c == 0x00) M.pos00 = S.pos;
@@ -417,7 +417,7 @@ P8_HD inline void pic_bit(State& S, Out& o) {
 }
 
 // ---------------------------------------------------------------- record models (:4204-4474)
-P8_HD inline void record_byte(State& S) {
+P8_COLD P8_HD inline void record_byte(State& S) {
   const Tables& T = *S.T;
   RecordM& M = S.record;
   const u32 c4 = S.c4;
@@ -573,7 +573,7 @@ P8_HD inline void record_core(State& S, Out& o, Rnd& rnd) {
   cm_mix(M.cp, o, rnd, y, c0, bpos, c1);
   for (int k = 0; k < 12; ++k) record_small(S, o, k);
 }
-P8_HD inline void record1_byte(State& S) {
+P8_COLD P8_HD inline void record1_byte(State& S) {
   const Tables& T = *S.T;
   Record1M& M = S.record1;
     const u32 c4 = S.c4;
@@ -614,7 +614,7 @@ P8_HD inline void record1_bit(State& S, Out& o, Rnd& rnd) {
 // wordModel at a byte boundary (:3873-4104) in three pieces: word_update changes the state (one lane), word_contexts is the pure
 // list of the 57 contexts (a warp can share it: CtxSel), word_finish applies the sentence-end shift the reference does between
 // contexts 41 and 42 (the contexts after it use the shifted words, computed locally).
-P8_HD inline void word_update(State& S) {
+P8_COLD P8_HD inline void word_update(State& S) {
   const Tables& T = *S.T;
   WordM& M = S.word;
   const u32 c4 = S.c4;
@@ -815,7 +815,7 @@ P8_HD inline void word_byte(State& S) {
 }
 
 // ---------------------------------------------------------------- nest model (:4107-4181)
-P8_HD inline void nest_byte(State& S) {
+P8_COLD P8_HD inline void nest_byte(State& S) {
   NestM& M = S.nest;
   const u32 c4 = S.c4;
   const int c = (int)(c4 & 255);
@@ -885,7 +885,7 @@ P8_HD inline void nest_byte(State& S) {
 }
 
 // ---------------------------------------------------------------- indirect model (:7548-7612)
-P8_HD inline void indirect_byte(State& S) {
+P8_COLD P8_HD inline void indirect_byte(State& S) {
   IndirectM& M = S.indirect;
   const u32 c4 = S.c4;
   const u32 d = c4 & 0xffff;
@@ -925,7 +925,7 @@ P8_HD inline void indirect_byte(State& S) {
 }
 
 // ---------------------------------------------------------------- DMC forest (:7777-7822)
-P8_HD inline void dmc_reset(Dmc& d, u32 th_start) {   // resetstategraph (:7655-7677)
+P8_COLD P8_HD inline void dmc_reset(Dmc& d, u32 th_start) {   // resetstategraph (:7655-7677)
   d.top = d.curr = d.extra = 0;
   d.threshold = th_start;
   d.threshold_fine = th_start << 11;
@@ -978,7 +978,7 @@ P8_HD inline void xml_detect(State& S, u32& type, u32 length, u32 c8, u8 B) {   
 }
 P8_HD inline void xml_clear(XmlTag& t) { t.name = t.length = 0; t.level = 0; t.end_tag = t.empty = 0; t.pad[0] = t.pad[1] = 0; t.c_data = t.c_length = t.c_type = 0;
   for (int i = 0; i < 4; ++i) t.a_name[i] = t.a_value[i] = t.a_length[i] = 0; t.a_index = 0; }
-P8_HD inline void xml_byte(State& S) {
+P8_COLD P8_HD inline void xml_byte(State& S) {
   XmlM& M = S.xml;
   enum { None, ReadTagName, ReadTag, ReadAttributeName, ReadAttributeValue, ReadContent, ReadCDATA, ReadComment };
   const u32 c4 = S.c4;

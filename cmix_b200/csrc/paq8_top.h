@@ -30,7 +30,7 @@ enum { TP_Unknown, TP_ReadingWord, TP_PossibleHyphenation, TP_WasAbbreviation, T
 // TextModel::Update (:3187-3375) in pieces so that the three stemmers of a completed word can run side by side on the device:
 // text_update_a does everything up to them (returns 1 when they are due), text_stem(lang) is one stemmer on its copy of the
 // word, text_update_b applies their verdicts and finishes the byte. text_update is the three in order.
-P8_HD inline void text_else_rest(State& S, u8 c, u8 pC) {
+P8_COLD P8_HD inline void text_else_rest(State& S, u8 c, u8 pC) {
   TextM& M = S.text;
     bool skip = false;
     int stage = 0;   // fall-through emulation: 1 = sentence end, 2 = segment end, 3 = new line, 4 = white space
@@ -134,7 +134,7 @@ P8_HD inline void text_else_rest(State& S, u8 c, u8 pC) {
       tseg(M, 0).num_count++; tsen(M, 0).num_count++;
     }
   }
-P8_HD inline void text_tail(State& S, u8 c) {
+P8_COLD P8_HD inline void text_tail(State& S, u8 c) {
   TextM& M = S.text;
   if (M.last_newline == 1) M.first_char = (M.lang_id != LANG_UNKNOWN) ? c : (u8)imin(c, 96);
   if (M.last_nest > 512) M.nest_hash = 0;
@@ -147,7 +147,7 @@ P8_HD inline void text_tail(State& S, u8 c) {
   S.st_text_first = M.first_letter;
   S.st_text_mask = (u8)(M.masks[1] & 0xFF);
 }
-P8_HD inline int text_update_a(State& S) {
+P8_COLD P8_HD inline int text_update_a(State& S) {
   const Tables& T = *S.T;
   TextM& M = S.text;
   M.last_upper = umin(0xFF, M.last_upper + 1); M.mask_upper <<= 1;
@@ -216,7 +216,7 @@ P8_HD inline int text_update_a(State& S) {
   text_tail(S, c);
   return 0;
 }
-P8_HD inline void text_stem(State& S, int i) {   // i = LANG_EN .. LANG_DE
+P8_COLD P8_HD inline void text_stem(State& S, int i) {   // i = LANG_EN .. LANG_DE
   TextM& M = S.text;
   Word& w = tw(M, i, 0);
   M.stem_ok[i - 1] = (u8)(i == LANG_EN ? StemEN::stem(w) : i == LANG_FR ? StemFR::stem(w) : StemDE::stem(w));
@@ -226,7 +226,7 @@ P8_HD inline void text_stem_mid(State& S) {      // between the rounds: the list
   for (int i = (int)M.stem_split - 1; i > LANG_UNKNOWN; --i)
     if (i != M.lang_id) word_copy(tw(M, i, 0), P8_CW);
 }
-P8_HD inline void text_update_b(State& S) {
+P8_COLD P8_HD inline void text_update_b(State& S) {
   TextM& M = S.text;
   const u8 c = (u8)lower((u8)buf(S, 1)), pC = (u8)buf(S, 2);
   for (int i = LANG_COUNT - 1; i > LANG_UNKNOWN; --i)
@@ -421,7 +421,7 @@ P8_HD inline u32 exe_cxt(const State& S, int i, int x) {   // execxt (:7263-7271
   return (u32)(prefix | opcode << 4 | modrm << 12 | x << 20 | sib << (28 - 6));
 }
 P8_HD inline u32 exe_opn(const ExeM& M, u32 n) { return M.cache[(M.cache_index - n) & 31]; }
-P8_HD inline void exe_byte(State& S) {
+P8_COLD P8_HD inline void exe_byte(State& S) {
   const Tables& T = *S.T;
   ExeM& M = S.exe;
   Instr& op = M.op;
@@ -716,7 +716,7 @@ P8_HD inline void linear_bit(State& S, Out& o) {
 P8_HD inline u32 le4(const State& S, int i) { return (u32)buf(S, i) + 256u * (u32)buf(S, i - 1) + 65536u * (u32)buf(S, i - 2) + 16777216u * (u32)buf(S, i - 3); }
 P8_HD inline int le2(const State& S, int i) { return buf(S, i) + 256 * buf(S, i - 1); }
 P8_HD inline u32 be4(const State& S, int i) { return (u32)buf(S, i - 3) + 256u * (u32)buf(S, i - 2) + 65536u * (u32)buf(S, i - 1) + 16777216u * (u32)buf(S, i); }
-P8_HD inline void detect_byte(State& S) {
+P8_COLD P8_HD inline void detect_byte(State& S) {
   // JPEG: SOI followed by a plausible marker (:6046-6049)
   if (S.filetype != FT_EXE && buf(S, 4) == 0xFF && buf(S, 3) == 0xD8 && buf(S, 2) == 0xFF &&
       ((buf(S, 1) & 0xFE) == 0xC0 || buf(S, 1) == 0xC4 || (buf(S, 1) >= 0xDB && buf(S, 1) <= 0xFE))) S.error |= ERR_UNSUPPORTED_BLOCK;
@@ -774,7 +774,7 @@ P8_HD inline int mixer_predict(const Tables& T, Mixer& m, int y, u16* codes) {  
 }
 
 // block header parsing in front of contextModel2 (:8116-8134): filetype and bytes remaining of the current block
-P8_HD inline void block_parse(State& S) {
+P8_COLD P8_HD inline void block_parse(State& S) {
   --S.size;
   ++S.blpos;
   if (S.size == -1) { S.info = 0; S.ft2 = buf(S, 1); }
@@ -794,7 +794,7 @@ P8_HD inline void block_parse(State& S) {
   if (S.filetype == FT_JPEG || (S.filetype >= FT_IMAGE1 && S.filetype <= FT_AUDIO)) S.error |= ERR_UNSUPPORTED_BLOCK;
   detect_byte(S);
 }
-P8_HD inline void ordern_byte(State& S) {   // :8140-8152
+P8_COLD P8_HD inline void ordern_byte(State& S) {   // :8140-8152
   const u8 B = (u8)S.c4;
   S.cxt[15] = is_alpha(B) ? (u32)combine64(S.cxt[15], (u64)lower(B)) : 0;
   cm2_set(S.cm, S.cxt[15]);
