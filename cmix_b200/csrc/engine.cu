@@ -259,7 +259,6 @@ int BuildSharedTablesLocked(int device, SharedTables& g_tables) {
   CK(cudaMemcpyToSymbol(c_ivmap, ivmap, sizeof ivmap));
   CK(cudaMemcpyToSymbol(c_mixer_sel, msel, sizeof msel));
   CK(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallState)));
-  CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(mix_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared3)));
   CK(cudaFuncSetAttribute(mix_predict_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MixShared)));
   CK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmShared)));

@@ -269,161 +269,14 @@ __device__ float final_stage(MixShared& sh, const Tables& T, SseState& sse, int 
   return p;
 }
 
-#define MIX_PROF(slot) do { if (prof_on) { const long long now_ = clock64(); a.prof[slot] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
-
-// Bulk kernel: cluster of 2 CTAs per stream.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MIX_THREADS, 1)
-mix_kernel(const ChunkArgs* __restrict__ args_all, Tables T) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const ChunkArgs a = args_all[blockIdx.x / 2];
-  StreamState* st = a.st;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  MixShared& sh = *reinterpret_cast<MixShared*>(smem_raw);
-  MixShared* sh0 = cluster.map_shared_rank(&sh, 0);     // CTA 0's shared memory (DSMEM)
-  MixShared* sh1 = cluster.map_shared_rank(&sh, 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = rank * MIX_PER_CTA;                     // first layer-0 mixer owned by this CTA
-
-  if (tid < MIX_PER_CTA) sh.cur_slot[tid] = 0xffffffffu;
-  __syncthreads();
-
-  const u64 n_bits = (u64)a.n_bytes * 8;
-  const bool prof_on = a.prof != nullptr && rank == 0 && tid == 0;
-  long long tprev = clock64();
-  for (u64 t = 0; t < n_bits; ++t) {
-    const int bit = (a.bytes[t >> 3] >> (7 - (t & 7))) & 1;
-    // ---------------- B0: stage inputs, resolve rows, make them resident ----------------
-    stage_inputs(sh.x, T, a.ext ? a.ext + t * N_EXT : nullptr, a.small_x + t * SMALL_X_PITCH, a.lstm_x[2 * t], tid, MIX_THREADS);
-    if (tid < SEL_PITCH) sh.sel[tid] = tid < N_MIXERS ? a.sel[t * SEL_PITCH + tid] : 0;
-    __syncthreads();
-    MIX_PROF(0);
-    if (tid == 0) sh.sel[12] = aux_context(sh.x);        // layer-0 mixer 12 is selected by auxiliary_context_
-    __syncthreads();
-    if (tid < MIX_PER_CTA) {
-      MixerState& m = st->mixer[m0 + tid];
-      sh.want_slot[tid] = resolve_slot(m, sh.sel[m0 + tid]);
-    } else if (rank == 0 && tid >= 32 && tid < 32 + N_L1 + 1) {
-      const int i = tid - 32;                            // layer-1 mixers 0..19, then the layer-2 mixer
-      MixerState& m = st->mixer[N_L0 + i];
-      sh.slot1[i] = resolve_slot(m, sh.sel[N_L0 + i]);
-    }
-    __syncthreads();
-    MIX_PROF(1);
-    for (int i = 0; i < MIX_PER_CTA; ++i) {              // evict + load rows whose selector moved
-      const u32 want = sh.want_slot[i], cur = sh.cur_slot[i];
-      if (want != cur) {
-        MixerState& m = st->mixer[m0 + i];
-        float4* srow = reinterpret_cast<float4*>(sh.rows[i]);
-        if (cur != 0xffffffffu) {
-          float4* g = reinterpret_cast<float4*>(m.rows + (size_t)cur * ROW_PITCH_L0);
-          for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) g[k] = srow[k];
-        }
-        const float4* g = reinterpret_cast<const float4*>(m.rows + (size_t)want * ROW_PITCH_L0);
-        for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) srow[k] = g[k];
-      }
-    }
-    if (rank == 0) {                                     // layer-1/2 rows are tiny: fetch every bit
-      for (int k = tid; k < N_L1 * ROW_PITCH_L1; k += MIX_THREADS) {
-        const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
-        sh.l1row[i][c] = st->mixer[N_L0 + i].rows[(size_t)sh.slot1[i] * ROW_PITCH_L1 + c];
-      }
-      if (tid < ROW_PITCH_L2) sh.l2row[tid] = st->mixer[N_L0 + N_L1].rows[(size_t)sh.slot1[N_L1] * ROW_PITCH_L2 + tid];
-    }
-    __syncthreads();
-    MIX_PROF(2);
-    if (tid < MIX_PER_CTA) sh.cur_slot[tid] = sh.want_slot[tid];
-    // ---------------- B1: the 13 serial dot-product chains of this CTA ----------------
-    if (warp == 0) {
-      if (lane < MIX_PER_CTA) {
-        const float p = chain_l0(sh.x, sh.rows[lane]);
-        sh0->mains[m0 + lane] = p;                       // DSMEM store into CTA 0
-      }
-    } else {
-      // meanwhile: publish this CTA's extra-input weights to CTA 0
-      for (int k = tid - 32; k < MIX_PER_CTA * N_L0; k += MIX_THREADS - 32) {
-        const int i = k / N_L0, c = k - i * N_L0;
-        sh0->we[m0 + i][c] = sh.rows[i][N_INPUTS + c];
-      }
-    }
-    MIX_PROF(3);
-    cluster.sync();
-    MIX_PROF(4);
-    // ---------------- B2: CTA 0 finishes the network and computes the SGD coefficients ----------------
-    if (rank == 0 && warp == 0) {
-      const float p = final_stage(sh, T, st->sse, lane);
-      if (lane == 0) {
-        const float ov = a.lstm_x[2 * t + 1];
-        a.p_out[t] = ov >= 0.0f ? ov : p;                // vocabulary override (predictor.cpp:415-417)
-      }
-      __syncwarp();
-      const float decay = a.decay[t];
-      if (lane < N_L0) {
-        u32 shr;
-        const float u = mixer_update_coeff(st->mixer[lane], lane < MIX_PER_CTA ? sh.cur_slot[lane] : sh1->cur_slot[lane - MIX_PER_CTA],
-                                           decay, sh.mixp[lane], bit, &shr);
-        sh.upd[lane] = u; sh1->upd[lane] = u;
-        if (lane < MIX_PER_CTA) sh.shrink[lane] = shr; else sh1->shrink[lane - MIX_PER_CTA] = shr;
-        sh1->x[N_INPUTS + lane] = sh.x[N_INPUTS + lane];   // the 26 extra inputs
-      }
-      if (lane < N_L1 + 1) {
-        u32 shr;
-        const int mi = N_L0 + lane;
-        sh.upd1[lane] = mixer_update_coeff(st->mixer[mi], sh.slot1[lane], decay, sh.mixp[mi], bit, &shr);
-        sh.shrink1[lane] = shr;
-      }
-      if (lane == 0) sse_perceive(st->sse, bit);
-    }
-    MIX_PROF(5);
-    cluster.sync();
-    MIX_PROF(6);
-    // ---------------- B3: SGD on the resident rows (mixer.cpp:66-71) ----------------
-    for (int i = 0; i < MIX_PER_CTA; ++i) {
-      const float u = sh.upd[m0 + i];
-      const bool shr = sh.shrink[i] != 0;
-      float* row = sh.rows[i];
-      const int n = N_INPUTS + m0 + i;
-      for (int k = tid; k < n; k += MIX_THREADS) {
-        float w = XM_FSUB(row[k], XM_FMUL(u, sh.x[k]));
-        if (shr) w = XM_FMUL(w, 1.0f - 3.0e-6f);
-        row[k] = w;
-      }
-    }
-    if (rank == 0) {
-      for (int k = tid; k < (N_L1 + 1) * ROW_PITCH_L1; k += MIX_THREADS) {
-        const int i = k / ROW_PITCH_L1, c = k - i * ROW_PITCH_L1;
-        float w, xin; int n;
-        if (i < N_L1) { n = L1_IN + i; w = sh.l1row[i][c]; xin = c < L1_IN ? sh.in1[c] : sh.l1extra[c - L1_IN]; }
-        else { n = L2_IN; w = sh.l2row[c]; xin = sh.in2[c]; }
-        if (c < n) {
-          w = XM_FSUB(w, XM_FMUL(sh.upd1[i], xin));
-          if (sh.shrink1[i]) w = XM_FMUL(w, 1.0f - 3.0e-6f);
-          st->mixer[N_L0 + i].rows[(size_t)sh.slot1[i] * ROW_PITCH_L1 + c] = w;
-        }
-      }
-    }
-    __syncthreads();
-    MIX_PROF(7);
-  }
-  // flush resident rows so that HBM holds the complete state between launches
-  for (int i = 0; i < MIX_PER_CTA; ++i) {
-    const u32 cur = sh.cur_slot[i];
-    if (cur != 0xffffffffu) {
-      float4* g = reinterpret_cast<float4*>(st->mixer[m0 + i].rows + (size_t)cur * ROW_PITCH_L0);
-      const float4* srow = reinterpret_cast<const float4*>(sh.rows[i]);
-      for (int k = tid; k < ROW_PITCH_L0 / 4; k += MIX_THREADS) g[k] = srow[k];
-    }
-  }
-  if (rank == 0 && tid == 0) st->bits_done += n_bits;
-  cluster.sync();
-}
+// (The first bulk kernel, a barrier-per-phase cluster kernel, lived here through round 1; mixer_v3.cuh replaced it. History: DESIGN.md §4.1.)
 
 }  // namespace cmixb200
 
 // ---------------------------------------------------------------------------
 // Lock-step halves (host calls Predictor::Predict / Perceive bit by bit, e.g. the
 // reference's Decoder, coder/decoder.cpp:20-39). Single CTA, rows stay in HBM.
-// Same arithmetic as mix_kernel; intermediate vectors are parked in StreamState.
+// Same arithmetic as the bulk kernel (mixer_v3.cuh); intermediate vectors are parked in StreamState.
 namespace cmixb200 {
 
 // ---------------------------------------------------------------------------------------------
