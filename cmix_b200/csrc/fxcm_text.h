@@ -235,15 +235,6 @@ struct Word {
   }
 };
 
-// Tables of suffixes / words walked in a loop keep the length and the deciding character of every entry next to the string, so
-// that a candidate that cannot match costs no read of the string itself (on the device the strings live in global memory).
-FX_HD inline bool ends_tab(const Word& w, const char* suf, int n, char last) {      // == w.ends(suf) with n = strlen(suf), last = suf[n-1]
-  return w.len() > (u32)n && w.L[w.e] == (u8)last && bytes_eq(&w.L[w.e - n + 1], suf, n - 1);
-}
-FX_HD inline bool is_tab(const Word& w, const char* word, int n, char first) {      // == w.is(word) with n = strlen(word), first = word[0]
-  return (int)(w.e - w.s + (w.L[w.s] != 0)) == n && w.L[w.s] == (u8)first && bytes_eq(&w.L[w.s], word, n);
-}
-
 FX_HD inline bool in_set(int c, const char* set) { for (; *set; ++set) if ((u8)*set == (u8)c) return true; return false; }
 FX_HD inline bool vowel(int c) { return in_set(c, "aeiouy"); }
 
@@ -365,16 +356,14 @@ struct Stemmer {
   }
   FX_HD static bool step1b(Word& w, u32 r1) {
     const char* suf[6] = {"eedly", "eed", "ed", "edly", "ing", "ingly"};
-    const u8 len[6] = {5, 3, 2, 4, 3, 5};
-    const char last[6] = {'y', 'd', 'd', 'y', 'g', 'y'};
     const u32 typ[6] = {T_AdverbOfManner, 0, T_PastTense, T_AdverbOfManner | T_PastTense, T_PresentParticiple, T_AdverbOfManner | T_PresentParticiple};
     for (int i = 0; i < 6; ++i) {
-      if (!ends_tab(w, suf[i], len[i], last[i])) continue;
+      if (!w.ends(suf[i])) continue;
       if (i < 2) {
-        if (in_rn(w, r1, len[i])) w.e -= 1 + i * 2;
+        if (in_rn(w, r1, cstrlen(suf[i]))) w.e -= 1 + i * 2;
       } else {
         const u8 keep = w.e;
-        w.e -= len[i];
+        w.e -= cstrlen(suf[i]);
         if (!has_vowel(w)) { w.e = keep; return false; }
         if (w.ends("at") || w.ends("bl") || w.ends("iz") || short_word(w)) w.append('e');
         else if (w.len() > 2) {
@@ -439,10 +428,8 @@ struct Stemmer {
                          T_AdverbOfManner | T_Noun | T_Suffix, T_AdverbOfManner, T_Suffix, 0, T_Noun | T_Suffix, T_AdverbOfManner, T_AdverbOfManner,
                          T_Noun | T_Suffix, 0, 0, T_AdverbOfManner, 0, 0, T_AdverbOfManner, T_AdverbOfManner};
     const u32 sfx[22] = {X_ION, X_ION | X_AL, X_NESS, X_NESS, X_NESS, X_ION | X_AL, 0, X_ITY, 0, X_ION, 0, X_ITY, 0, 0, X_ITY, 0, 0, 0, 0, 0, 0, 0};
-    const u8 len[22] = {7, 7, 7, 7, 7, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 4, 4, 4, 4, 4, 4, 3};
-    const char last[22] = {'n', 'l', 's', 's', 's', 'l', 'i', 'i', 'i', 'n', 'm', 'i', 'i', 'i', 'i', 'i', 'i', 'i', 'r', 'r', 'i', 'i'};
     for (int i = 0; i < 22; ++i)
-      if (ends_tab(w, from[i], len[i], last[i]) && in_rn(w, r1, len[i])) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; w.suffix |= sfx[i]; return true; }
+      if (w.ends(from[i]) && in_rn(w, r1, cstrlen(from[i]))) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; w.suffix |= sfx[i]; return true; }
     if (w.ends("logi") && in_rn(w, r1, 3)) { --w.e; return true; }
     if (w.ends("li")) {
       if (in_rn(w, r1, 2) && in_set(w.rat(2), "cdeghkmnrt")) { w.e -= 2; w.type |= T_AdverbOfManner; return true; }
@@ -465,10 +452,8 @@ struct Stemmer {
     const u32 typ[8] = {T_Suffix | T_Adjective, T_Suffix | T_Adjective, 0, 0, T_Noun | T_Suffix, T_Suffix | T_Adjective, T_AdjFull, T_Suffix};
     const u32 sfx[8] = {X_ION | X_AL, X_ION | X_AL, 0, 0, X_ITY, X_AL, 0, X_NESS};
     bool r = false;
-    const u8 len[8] = {7, 6, 5, 5, 5, 4, 3, 4};
-    const char last[8] = {'l', 'l', 'e', 'e', 'i', 'l', 'l', 's'};
     for (int i = 0; i < 8; ++i)
-      if (ends_tab(w, from[i], len[i], last[i]) && in_rn(w, r1, len[i])) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; w.suffix |= sfx[i]; r = true; break; }
+      if (w.ends(from[i]) && in_rn(w, r1, cstrlen(from[i]))) { w.swap_suffix(from[i], to[i]); w.type |= typ[i]; w.suffix |= sfx[i]; r = true; break; }
     if (w.ends("ative") && in_rn(w, r2, 5)) { w.e -= 5; w.type |= T_Suffix; w.suffix |= X_IVE; return true; }
     if (w.len() > 5 && w.ends("less")) { w.e -= 4; w.type |= T_AdjWithout; return true; }
     return r;
@@ -480,11 +465,9 @@ struct Stemmer {
                          T_Suffix | T_Noun, T_Suffix | T_Adjective, T_Suffix, 0, T_Suffix, T_Suffix};
     const u32 sfx[20] = {X_AL, X_NCE, X_NCE, 0, X_IC, X_Capable, X_Capable, X_NT, 0, 0, X_NT, 0, 0, 0, X_ITY, X_OUS, X_IVE, 0, X_ION, X_ION};
     bool r = false;
-    const u8 len[20] = {2, 4, 4, 2, 2, 4, 4, 3, 5, 4, 3, 2, 3, 3, 3, 3, 3, 3, 4, 4};
-    const char last[20] = {'l', 'e', 'e', 'r', 'c', 'e', 'e', 't', 't', 't', 't', 'u', 'm', 'e', 'i', 's', 'e', 'e', 'n', 'n'};
     for (int i = 0; i < 20; ++i) {
-      if (ends_tab(w, suf[i], len[i], last[i]) && in_rn(w, r2, len[i])) {
-        w.e -= len[i] - (i > 17);
+      if (w.ends(suf[i]) && in_rn(w, r2, cstrlen(suf[i]))) {
+        w.e -= cstrlen(suf[i]) - (i > 17);
         if (i != 10 || w.rat(0) != 'm') { w.type |= typ[i]; w.suffix |= sfx[i]; }
         if (i == 0 && w.ends("nti")) { --w.e; r = true; continue; }
         return true;
@@ -515,10 +498,8 @@ struct Stemmer {
       const u32 t[19] = {T_Noun | T_Plural, T_Noun | T_Plural, T_PresentParticiple, T_PresentParticiple, T_PresentParticiple, T_AdverbOfManner,
                          T_AdverbOfManner, T_Adjective, T_Adjective | T_AdverbOfManner, 0, T_AdverbOfManner, T_Noun, T_Noun, 0, T_Noun, T_Noun,
                          T_Noun, T_Noun | T_Plural, T_Noun};
-      const u8 len[19] = {4, 5, 5, 5, 5, 4, 6, 4, 5, 4, 6, 3, 4, 4, 5, 6, 4, 5, 5};
-      const char first[19] = {'s', 's', 'd', 'l', 't', 'i', 'g', 'u', 'e', 'o', 's', 's', 'n', 'h', 'a', 'c', 'b', 'a', 't'};
       for (int i = 0; i < 19; ++i)
-        if (is_tab(w, a[i], len[i], first[i])) {
+        if (w.is(a[i])) {
           if (i < 11) set_letters(w, b[i]);
           rehash(w);
           w.type |= t[i];
@@ -531,10 +512,8 @@ struct Stemmer {
     if (step1a(w)) r = true;
     {
       const char* a[8] = {"inning", "outing", "canning", "herring", "earring", "proceed", "exceed", "succeed"};
-      const u8 len[8] = {6, 6, 7, 7, 7, 7, 6, 7};
-      const char first[8] = {'i', 'o', 'c', 'h', 'e', 'p', 'e', 's'};
       for (int i = 0; i < 8; ++i)
-        if (is_tab(w, a[i], len[i], first[i])) { rehash(w); w.type |= i < 5 ? T_Noun : T_Verb; return r; }
+        if (w.is(a[i])) { rehash(w); w.type |= i < 5 ? T_Noun : T_Verb; return r; }
     }
     if (step1b(w, r1)) r = true;
     if (step1c(w)) r = true;
